@@ -1,0 +1,10 @@
+// Field sizes the library is instantiated for (H, W).  The reference takes any game_size; each size here costs one
+// instantiation of every kernel, so the list is the BASELINE.json configurations plus two small ones used by tests.
+// Add a line to support another size.
+#pragma once
+#define B2T_FOR_EACH_GEOMETRY(X) \
+    X(22, 10)                    \
+    X(16, 8)                     \
+    X(40, 20)                    \
+    X(10, 6)                     \
+    X(12, 5)

@@ -1,0 +1,267 @@
+// TEST INFRASTRUCTURE ONLY.  Runs the *same* game-core headers the CUDA kernels are built from
+// (drl-tetris_b200/csrc/b2t_{core,enum,game,rng}.cuh) on the CPU, one game at a time, through the identical HBM
+// word layout, so rule bugs are found in the GPU-less build container by diffing against the oracle
+// (tests/test_hostsim_vs_oracle.py).  Nothing in the product library links or calls this.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "b2t_game.cuh"
+#include "b2t_geoms.h"
+#include "b2t_rng.cuh"
+
+using namespace b2t;
+
+struct HSBase {
+    virtual ~HSBase() {}
+    virtual void reset(const int32_t* idx, int n, const uint32_t* seeds) = 0;
+    virtual void step(const int32_t* idx, int n, const uint8_t* player, const uint8_t* keys, const uint8_t* key_len, int lmax,
+                      int time_ms, int finalize, int8_t* reward, uint8_t* done, uint8_t* lines) = 0;
+    virtual void observe(const int32_t* idx, int n, uint8_t* field, uint8_t* vec, uint8_t* pidx) = 0;
+    virtual void scal(const int32_t* idx, int n, int32_t* out) = 0;
+    virtual int enumerate(const int32_t* idx, int n, const uint8_t* player, int bar_null, int kmax, int lmax, int32_t* K,
+                          uint8_t* keys, uint8_t* key_len) = 0;
+    virtual int expand(const int32_t* idx, int n, const uint8_t* player, int bar_null, int finalize, int time_ms, int kmax, int lmax,
+                       int32_t* K, uint8_t* keys, uint8_t* key_len, uint8_t* field, uint8_t* vec, uint8_t* pidx, int8_t* reward,
+                       uint8_t* done, uint8_t* lines) = 0;
+    virtual int flags(int game) = 0;
+};
+
+template <int KW> struct ListSink {
+    uint32_t* out;  // [cap][KW]
+    int cap, count, bad;
+    uint64_t fin[4];
+    void init(uint32_t* o, int c) { out = o; cap = c; count = 0; bad = 0; fin[0] = fin[1] = fin[2] = fin[3] = 0; }
+    B2T_HD void append(const Seq<KW>& s, bool b, bool is_fin) {
+        if (b) bad = 1;
+        if (count >= cap) { bad = 1; return; }
+        for (int i = 0; i < KW; i++) out[count * KW + i] = s.w[i];
+        if (is_fin) fin[count >> 6] |= 1ull << (count & 63);
+        count++;
+    }
+    B2T_HD void top(const Seq<KW>& s, bool b) { append(s, b, false); }
+    B2T_HD void finesse(const Seq<KW>& s, bool b) {
+        for (int k = 0; k < count; k++)
+            if ((fin[k >> 6] >> (k & 63)) & 1)
+                if (seq_equal<KW>(s, out + k * KW)) return;   // action_list.py:14: first occurrence wins
+        append(s, b, true);
+    }
+};
+
+template <int H, int W> struct HS : HSBase {
+    typedef Geo<H, W> G;
+    typedef typename G::col_t col_t;
+    static constexpr int KW = G::KEYW;
+    int n;
+    std::vector<uint32_t> state;  // uint4 state[NV][n]
+    PieceTables pt;
+    uint8_t map[7];
+    bool only_zs;
+    uint32_t piece_len, hole_len;
+    std::vector<uint8_t> piece_tab, hole_tab;
+    std::vector<uint8_t> row_ready;
+    double powtab[256];
+    Tabs tb;
+    col_t cols[2][G::NCOL];
+    uint32_t stream[2][G::SW];
+
+    HS(int n_, const uint8_t* map_, uint32_t plen, uint32_t hlen) : n(n_), piece_len(plen), hole_len(hlen) {
+        memcpy(map, map_, 7);
+        only_zs = true;
+        for (int i = 0; i < 7; i++) if (map[i] != 2 && map[i] != 3) only_zs = false;
+        make_piece_tables(pt);
+        piece_tab.assign((size_t)RNG_SEEDS * piece_len, 0);
+        hole_tab.assign((size_t)RNG_SEEDS * hole_len, 0);
+        row_ready.assign(RNG_SEEDS, 0);
+        for (int c = 0; c < 256; c++) powtab[c] = pow((double)c, 1.4 + c * 0.01);
+        tb.pcn = pt.pcn; tb.pcc = pt.pcc; tb.piece = piece_tab.data(); tb.hole = hole_tab.data(); tb.powtab = powtab;
+        tb.piece_len = piece_len; tb.hole_len = hole_len; tb.spawn_rots = 0;
+        for (int k = 0; k < 7; k++) tb.spawn_rots |= (uint32_t)pt.spawn_rot[k] << (2 * k);
+        state.assign((size_t)G::NV * 4 * n, 0);
+        Game<G, 1> g;
+        bind(g);
+        for (int i = 0; i < n; i++) { game_init(g); save(g, i); }
+    }
+    void bind(Game<G, 1>& g) {
+        for (int p = 0; p < 2; p++) {
+            g.b[p].cols = cols[p]; g.b[p].stream = stream[p];
+            board_init_walls<G, 1>(g.b[p]);
+        }
+    }
+    void ensure_row(uint32_t s16) {
+        if (row_ready[s16]) return;
+        static MT19937 mt;
+        fill_stream_row(mt, s16, map, only_zs, W, &piece_tab[(size_t)s16 * piece_len], piece_len, &hole_tab[(size_t)s16 * hole_len], hole_len);
+        row_ready[s16] = 1;
+    }
+    void load(Game<G, 1>& g, int gi) {
+        for (int v = 0; v < G::NV; v++)
+            for (int k = 0; k < 4; k++) game_put_word(g, 4 * v + k, state[((size_t)v * n + gi) * 4 + k]);
+        game_unpack(g);
+    }
+    void save(Game<G, 1>& g, int gi) {
+        game_pack(g);
+        for (int v = 0; v < G::NV; v++)
+            for (int k = 0; k < 4; k++) state[((size_t)v * n + gi) * 4 + k] = game_get_word(g, 4 * v + k);
+    }
+    void reset(const int32_t* idx, int cnt, const uint32_t* seeds) override {
+        Game<G, 1> g; bind(g);
+        for (int i = 0; i < cnt; i++) {
+            int gi = idx ? idx[i] : i;
+            ensure_row(seeds[i] & 0xFFFF);
+            load(g, gi);
+            game_reset(g, tb, seeds[i]);
+            save(g, gi);
+        }
+    }
+    void step(const int32_t* idx, int cnt, const uint8_t* player, const uint8_t* keys, const uint8_t* key_len, int lmax, int time_ms,
+              int finalize, int8_t* reward, uint8_t* done, uint8_t* lines) override {
+        Game<G, 1> g; bind(g);
+        for (int i = 0; i < cnt; i++) {
+            int gi = idx ? idx[i] : i;
+            load(g, gi);
+            uint32_t kw[KW];
+            pack_keys<KW>(keys + (size_t)i * lmax, key_len[i], kw);
+            int r;
+            bool d = game_perform<G, 1, KW>(g, tb, player[i], kw, key_len[i], finalize != 0, time_ms, &r);
+            if (reward) reward[i] = (int8_t)r;
+            if (done) done[i] = d;
+            if (lines) { lines[2 * i] = (uint8_t)g.p[0].reward; lines[2 * i + 1] = (uint8_t)g.p[1].reward; }
+            save(g, gi);
+        }
+    }
+    void obs_of(Game<G, 1>& g, uint8_t* field, uint8_t* vec, uint8_t* pidx) {
+        for (int p = 0; p < 2; p++) {
+            if (field)
+                for (int c = 0; c < H * W; c++) field[p * H * W + c] = (g.b[p].sw(c >> 5) >> (c & 31)) & 1;
+            if (vec) observe_vec(g.p[p], vec + p * VEC_LEN);
+            if (pidx) pidx[p] = (uint8_t)g.p[p].kind;
+        }
+        // cross-check the two board forms (columns vs stream)
+        for (int p = 0; p < 2; p++)
+            for (int y = 0; y < H; y++)
+                for (int x = 0; x < W; x++) {
+                    int a = (int)((g.b[p].col(x) >> (y + G::YB)) & 1), b = (g.b[p].sw((y * W + x) >> 5) >> ((y * W + x) & 31)) & 1;
+                    if (a != b) abort();
+                }
+    }
+    void observe(const int32_t* idx, int cnt, uint8_t* field, uint8_t* vec, uint8_t* pidx) override {
+        Game<G, 1> g; bind(g);
+        for (int i = 0; i < cnt; i++) {
+            load(g, idx ? idx[i] : i);
+            obs_of(g, field ? field + (size_t)i * 2 * H * W : nullptr, vec ? vec + (size_t)i * 2 * VEC_LEN : nullptr, pidx ? pidx + 2 * i : nullptr);
+        }
+    }
+    void scal(const int32_t* idx, int cnt, int32_t* out) override {
+        Game<G, 1> g; bind(g);
+        for (int i = 0; i < cnt; i++) {
+            load(g, idx ? idx[i] : i);
+            for (int p = 0; p < 2; p++) {
+                int32_t* s = out + ((size_t)i * 2 + p) * 8;
+                const PS& q = g.p[p];
+                s[0] = q.x; s[1] = q.y; s[2] = q.inc_count; s[3] = q.remaining; s[4] = q.combo_count; s[5] = q.next; s[6] = q.reward; s[7] = q.dead;
+            }
+        }
+    }
+    // enumerate one loaded game into packed list; returns K (after null handling), list at `lst` (cap KMAX+1)
+    int enum_game(Game<G, 1>& g, int player, int bar_null, uint32_t* lst, int cap, int* bad) {
+        ListSink<KW> sink;
+        int off = bar_null ? 0 : 1;
+        for (int i = 0; i < KW; i++) lst[i] = 0;   // slot 0 = null action when needed
+        sink.init(lst + off * KW, cap - off);
+        const PS& me = g.p[player];
+        if (me.kind <= 6) {
+            Enumerator<G, 1, KW, ListSink<KW>> e(g.b[player], tb, me.kind, sink);
+            e.run(me.rot);
+        }
+        *bad = sink.bad;
+        if (sink.count == 0) { for (int i = 0; i < KW; i++) lst[i] = 0; return 1; }
+        return sink.count + off;
+    }
+    static void unpack_seq(const uint32_t* w, uint8_t* keys, uint8_t* len, int lmax) {
+        int L = packed_len<KW>(w);
+        memset(keys, 0, lmax);
+        for (int i = 0; i < L && i < lmax; i++) keys[i] = (w[i >> 3] >> (4 * (i & 7))) & 15;
+        *len = (uint8_t)(L < lmax ? L : lmax);
+    }
+    int enumerate(const int32_t* idx, int cnt, const uint8_t* player, int bar_null, int kmax, int lmax, int32_t* K, uint8_t* keys,
+                  uint8_t* key_len) override {
+        Game<G, 1> g; bind(g);
+        std::vector<uint32_t> lst((size_t)(kmax + 1) * KW);
+        int nbad = 0;
+        for (int i = 0; i < cnt; i++) {
+            load(g, idx ? idx[i] : i);
+            int bad;
+            int k = enum_game(g, player[i], bar_null, lst.data(), kmax, &bad);
+            K[i] = k;
+            nbad += bad;
+            for (int a = 0; a < kmax; a++) {
+                uint8_t* dst = keys + ((size_t)i * kmax + a) * lmax;
+                if (a < k) unpack_seq(&lst[(size_t)a * KW], dst, &key_len[(size_t)i * kmax + a], lmax);
+                else { memset(dst, 0, lmax); key_len[(size_t)i * kmax + a] = 0; }
+            }
+        }
+        return nbad;
+    }
+    int expand(const int32_t* idx, int cnt, const uint8_t* player, int bar_null, int finalize, int time_ms, int kmax, int lmax, int32_t* K,
+               uint8_t* keys, uint8_t* key_len, uint8_t* field, uint8_t* vec, uint8_t* pidx, int8_t* reward, uint8_t* done,
+               uint8_t* lines) override {
+        Game<G, 1> g; bind(g);
+        std::vector<uint32_t> lst((size_t)(kmax + 1) * KW);
+        int nbad = 0;
+        for (int i = 0; i < cnt; i++) {
+            int gi = idx ? idx[i] : i;
+            load(g, gi);
+            int bad;
+            int k = enum_game(g, player[i], bar_null, lst.data(), kmax, &bad);
+            K[i] = k; nbad += bad;
+            for (int a = 0; a < kmax; a++) {
+                size_t o = (size_t)i * kmax + a;
+                uint8_t* dst = keys + o * lmax;
+                if (a >= k) { memset(dst, 0, lmax); key_len[o] = 0; continue; }
+                unpack_seq(&lst[(size_t)a * KW], dst, &key_len[o], lmax);
+                load(g, gi);
+                int r;
+                bool d = game_perform<G, 1, KW>(g, tb, player[i], &lst[(size_t)a * KW], packed_len<KW>(&lst[(size_t)a * KW]), finalize != 0, time_ms, &r);
+                if (reward) reward[o] = (int8_t)r;
+                if (done) done[o] = d;
+                if (lines) { lines[2 * o] = (uint8_t)g.p[0].reward; lines[2 * o + 1] = (uint8_t)g.p[1].reward; }
+                obs_of(g, field ? field + o * 2 * H * W : nullptr, vec ? vec + o * 2 * VEC_LEN : nullptr, pidx ? pidx + 2 * o : nullptr);
+            }
+        }
+        return nbad;
+    }
+    int flags(int gi) override {
+        Game<G, 1> g; bind(g);
+        load(g, gi);
+        return g.p[0].flags | g.p[1].flags;
+    }
+};
+
+extern "C" {
+void* hs_create(int n, int H, int W, const uint8_t* map, uint32_t piece_len, uint32_t hole_len) {
+#define X(h, w) if (H == h && W == w) return (HSBase*)new HS<h, w>(n, map, piece_len, hole_len);
+    B2T_FOR_EACH_GEOMETRY(X)
+#undef X
+    return nullptr;
+}
+void hs_destroy(void* h) { delete (HSBase*)h; }
+void hs_reset(void* h, const int32_t* idx, int n, const uint32_t* seeds) { ((HSBase*)h)->reset(idx, n, seeds); }
+void hs_step(void* h, const int32_t* idx, int n, const uint8_t* player, const uint8_t* keys, const uint8_t* key_len, int lmax, int time_ms,
+             int finalize, int8_t* reward, uint8_t* done, uint8_t* lines) {
+    ((HSBase*)h)->step(idx, n, player, keys, key_len, lmax, time_ms, finalize, reward, done, lines);
+}
+void hs_observe(void* h, const int32_t* idx, int n, uint8_t* field, uint8_t* vec, uint8_t* pidx) { ((HSBase*)h)->observe(idx, n, field, vec, pidx); }
+void hs_scal(void* h, const int32_t* idx, int n, int32_t* out) { ((HSBase*)h)->scal(idx, n, out); }
+int hs_enumerate(void* h, const int32_t* idx, int n, const uint8_t* player, int bar_null, int kmax, int lmax, int32_t* K, uint8_t* keys,
+                 uint8_t* key_len) {
+    return ((HSBase*)h)->enumerate(idx, n, player, bar_null, kmax, lmax, K, keys, key_len);
+}
+int hs_expand(void* h, const int32_t* idx, int n, const uint8_t* player, int bar_null, int finalize, int time_ms, int kmax, int lmax,
+              int32_t* K, uint8_t* keys, uint8_t* key_len, uint8_t* field, uint8_t* vec, uint8_t* pidx, int8_t* reward, uint8_t* done,
+              uint8_t* lines) {
+    return ((HSBase*)h)->expand(idx, n, player, bar_null, finalize, time_ms, kmax, lmax, K, keys, key_len, field, vec, pidx, reward, done, lines);
+}
+int hs_flags(void* h, int game) { return ((HSBase*)h)->flags(game); }
+}
