@@ -1,0 +1,506 @@
+// b200tetris — C ABI (include/b200tetris.h): handle lifetime, argument checking, launch plumbing, pinned staging for
+// the *_host entry points.  No game logic lives here and there is no CPU path: every call ends in a kernel launch.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200tetris.h"
+#include "b2t_geoms.h"
+#define B2T_COMMON_KERNELS
+#include "b2t_kernels.cuh"
+
+using namespace b2t;
+
+#define X(h, w) const GeomOps* b2t_geom_ops_##h##_##w();
+B2T_FOR_EACH_GEOMETRY(X)
+#undef X
+
+static const GeomOps* find_geom(int H, int W) {
+#define X(h, w) if (H == h && W == w) return b2t_geom_ops_##h##_##w();
+    B2T_FOR_EACH_GEOMETRY(X)
+#undef X
+    return nullptr;
+}
+
+static thread_local std::string g_create_error;
+
+struct Arena {  // grow-only pinned host + device scratch for the *_host calls
+    unsigned char* h = nullptr;
+    unsigned char* d = nullptr;
+    size_t cap = 0, at = 0;
+    cudaError_t reserve(size_t bytes) {
+        at = 0;
+        if (bytes <= cap) return cudaSuccess;
+        if (h) cudaFreeHost(h);
+        if (d) cudaFree(d);
+        h = d = nullptr; cap = 0;
+        bytes = (bytes + (1u << 20)) & ~((size_t)(1u << 20) - 1);
+        cudaError_t e = cudaMallocHost((void**)&h, bytes);
+        if (e != cudaSuccess) return e;
+        e = cudaMalloc((void**)&d, bytes);
+        if (e != cudaSuccess) return e;
+        cap = bytes;
+        return cudaSuccess;
+    }
+    size_t take(size_t bytes) { size_t o = at; at += (bytes + 255) & ~(size_t)255; return o; }
+    void release() { if (h) cudaFreeHost(h); if (d) cudaFree(d); h = d = nullptr; cap = 0; }
+};
+
+struct b2t_handle {
+    b2t_config cfg;
+    const GeomOps* ops = nullptr;
+    uint4* state = nullptr;
+    size_t state_vecs = 0;
+    uint4* snap[B2T_SNAPSHOT_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t* plc = nullptr;
+    int32_t* kcache = nullptr;
+    int32_t* scan_sums = nullptr;
+    int32_t* d_total = nullptr;
+    uint8_t* piece_tab = nullptr;
+    uint8_t* hole_tab = nullptr;
+    double* powtab = nullptr;
+    unsigned long long* stats = nullptr;
+    uint4* xfer = nullptr;   // one game's vectors for export/import
+    DevTabs tabs;
+    Arena in, out;
+    bool enumerated = false;
+    std::string err;
+};
+
+static int fail(b2t_handle* h, int code, const char* fmt, const char* a = "", long long b = 0) {
+    char buf[512];
+    snprintf(buf, sizeof buf, fmt, a, b);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) return fail(h, B2T_ERR_CUDA, "CUDA error: %s (line %lld)", cudaGetErrorString(e_), __LINE__); \
+    } while (0)
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" {
+
+const char* b2t_last_error(const b2t_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int b2t_destroy(b2t_handle* h) {
+    if (!h) return B2T_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaFree(h->state);
+    for (auto s : h->snap) cudaFree(s);
+    cudaFree(h->plc); cudaFree(h->kcache); cudaFree(h->scan_sums); cudaFree(h->d_total);
+    cudaFree(h->piece_tab); cudaFree(h->hole_tab); cudaFree(h->powtab); cudaFree(h->stats); cudaFree(h->xfer);
+    h->in.release(); h->out.release();
+    delete h;
+    return B2T_OK;
+}
+
+int b2t_create(const b2t_config* cfg, b2t_handle** out) {
+    b2t_handle* h = nullptr;
+    if (!cfg || !out) return fail(h, B2T_ERR_ARG, "b2t_create: NULL argument%s");
+    *out = nullptr;
+    if (cfg->n_games < 1) return fail(h, B2T_ERR_ARG, "b2t_create: n_games must be >= 1%s");
+    if (cfg->n_players != 2) return fail(h, B2T_ERR_UNSUPPORTED, "b2t_create: only n_players == 2 is built%s");
+    for (int i = 0; i < 7; i++)
+        if (cfg->piece_map[i] > 6) return fail(h, B2T_ERR_ARG, "b2t_create: piece_map entries must be 0..6%s");
+    const GeomOps* ops = find_geom(cfg->height, cfg->width);
+    if (!ops) return fail(h, B2T_ERR_UNSUPPORTED, "b2t_create: field size %s%lld not instantiated (csrc/b2t_geoms.h)", "H*1000+W=", cfg->height * 1000LL + cfg->width);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(h, B2T_ERR_CUDA, "b2t_create: no CUDA device — this library has no CPU path%s");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(h, B2T_ERR_ARG, "b2t_create: bad device ordinal%s");
+    h = new b2t_handle();
+    h->cfg = *cfg;
+    h->ops = ops;
+    if (h->cfg.time_ms_per_action <= 0) h->cfg.time_ms_per_action = 400;
+    if (h->cfg.piece_stream_len <= 0) h->cfg.piece_stream_len = 4096;
+    if (h->cfg.hole_stream_len <= 0) h->cfg.hole_stream_len = 512;
+    if (h->cfg.piece_stream_len < 4) h->cfg.piece_stream_len = 4;
+#define CKC(call)                                                                        \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            fail(nullptr, B2T_ERR_CUDA, "b2t_create: CUDA error: %s (line %lld)", cudaGetErrorString(e_), __LINE__); \
+            b2t_destroy(h);                                                              \
+            return B2T_ERR_CUDA;                                                         \
+        }                                                                                \
+    } while (0)
+    CKC(cudaSetDevice(cfg->device));
+    CKC(ops->prepare());
+    const size_t n = (size_t)cfg->n_games;
+    h->state_vecs = (size_t)ops->NV * n;
+    CKC(cudaMalloc((void**)&h->state, h->state_vecs * sizeof(uint4)));
+    CKC(cudaMalloc((void**)&h->kcache, n * sizeof(int32_t)));
+    CKC(cudaMemset(h->kcache, 0, n * sizeof(int32_t)));
+    CKC(cudaMalloc((void**)&h->scan_sums, (size_t)SCAN_TILE * sizeof(int32_t)));
+    CKC(cudaMalloc((void**)&h->d_total, 64));
+    CKC(cudaMalloc((void**)&h->stats, STAT_SLICES * STAT_WORDS * sizeof(unsigned long long)));
+    CKC(cudaMemset(h->stats, 0, STAT_SLICES * STAT_WORDS * sizeof(unsigned long long)));
+    CKC(cudaMalloc((void**)&h->xfer, (size_t)ops->NV * sizeof(uint4)));
+    const size_t plen = (size_t)h->cfg.piece_stream_len, hlen = (size_t)h->cfg.hole_stream_len;
+    CKC(cudaMalloc((void**)&h->piece_tab, plen * RNG_SEEDS));
+    CKC(cudaMalloc((void**)&h->hole_tab, hlen * RNG_SEEDS));
+    CKC(cudaMalloc((void**)&h->powtab, 256 * sizeof(double)));
+    {
+        double pw[256];
+        for (int c = 0; c < 256; c++) pw[c] = pow((double)c, 1.4 + c * 0.01);  // Combo.cpp:41, host libm
+        CKC(cudaMemcpy(h->powtab, pw, sizeof pw, cudaMemcpyHostToDevice));
+    }
+    {
+        PieceTables pt;
+        make_piece_tables(pt);
+        memcpy(h->tabs.pcn, pt.pcn, sizeof pt.pcn);
+        memcpy(h->tabs.pcc, pt.pcc, sizeof pt.pcc);
+        h->tabs.spawn_rots = 0;
+        for (int k = 0; k < 7; k++) h->tabs.spawn_rots |= (uint32_t)pt.spawn_rot[k] << (2 * k);
+        h->tabs.piece = h->piece_tab; h->tabs.hole = h->hole_tab; h->tabs.powtab = h->powtab;
+        h->tabs.piece_len = (uint32_t)plen; h->tabs.hole_len = (uint32_t)hlen;
+    }
+    {
+        PieceMap pm;
+        bool only_zs = true;  // set_pieces, PythonHandle.h:116-121
+        for (int i = 0; i < 7; i++) { pm.m[i] = cfg->piece_map[i]; if (pm.m[i] != 2 && pm.m[i] != 3) only_zs = false; }
+        pm.m[7] = 0;
+        fill_tables_kernel<<<RNG_SEEDS / 64, 64>>>(h->piece_tab, (uint32_t)plen, h->hole_tab, (uint32_t)hlen, pm, only_zs ? 1 : 0, cfg->width);
+        CKC(cudaGetLastError());
+    }
+    CKC(ops->launch_init(h->state, cfg->n_games, 0));
+    CKC(cudaDeviceSynchronize());
+    *out = h;
+    return B2T_OK;
+}
+
+int b2t_get_info(const b2t_handle* h, b2t_info* out) {
+    if (!h || !out) return B2T_ERR_ARG;
+    out->kmax = h->ops->KMAX; out->lmax = h->ops->LMAX;
+    out->state_bytes = h->ops->NV * 16;
+    out->obs_bytes = 2 * (h->ops->H * h->ops->W + B2T_VEC_LEN + 1);
+    return B2T_OK;
+}
+
+static void base_params(b2t_handle* h, KParams& p) {
+    memset(&p, 0, sizeof p);
+    p.state = h->state; p.n_games = h->cfg.n_games; p.tabs = h->tabs; p.stats = h->stats;
+    p.plc = h->plc; p.kcache = h->kcache; p.elapsed = h->cfg.time_ms_per_action;
+}
+static int check_obs(b2t_handle* h, const b2t_obs& o) {
+    if (!aligned16(o.d_field) || !aligned16(o.d_vec) || !aligned16(o.d_piece_idx) || !aligned16(o.d_scalars))
+        return fail(h, B2T_ERR_ARG, "observation pointers must be 16-byte aligned%s");
+    return B2T_OK;
+}
+static void set_obs(KParams& p, const b2t_obs& o) { p.field = o.d_field; p.vec = o.d_vec; p.piece_idx = o.d_piece_idx; p.scalars = o.d_scalars; }
+
+int b2t_reset(b2t_handle* h, const int32_t* d_idx, int32_t n, const uint32_t* d_seeds, void* stream) {
+    if (!h) return B2T_ERR_ARG;
+    if (n < 0 || n > h->cfg.n_games || !d_seeds) return fail(h, B2T_ERR_ARG, "b2t_reset: bad n or NULL seeds%s");
+    CK(cudaSetDevice(h->cfg.device));
+    KParams p; base_params(h, p);
+    p.idx = d_idx; p.n = n; p.seeds = d_seeds; p.flags = KF_RESET | KF_STORE;
+    CK(h->ops->launch_game(p, n, (cudaStream_t)stream));
+    return B2T_OK;
+}
+
+int b2t_step(b2t_handle* h, const b2t_step_args* a, void* stream) {
+    if (!h || !a) return B2T_ERR_ARG;
+    if (a->n < 0 || a->n > h->cfg.n_games || !a->d_player) return fail(h, B2T_ERR_ARG, "b2t_step: bad n or NULL d_player%s");
+    if (!a->d_placement && (!a->d_keys || !a->d_key_len || a->lmax < 1)) return fail(h, B2T_ERR_ARG, "b2t_step: need d_placement or d_keys+d_key_len+lmax%s");
+    if (a->d_placement && !h->enumerated) return fail(h, B2T_ERR_STATE, "b2t_step: d_placement needs a prior b2t_enumerate/b2t_expand%s");
+    if (int r = check_obs(h, a->obs)) return r;
+    CK(cudaSetDevice(h->cfg.device));
+    KParams p; base_params(h, p);
+    p.idx = a->d_game_idx; p.n = a->n; p.player = a->d_player;
+    p.keys = a->d_keys; p.key_len = a->d_key_len; p.lmax = a->lmax; p.placement = a->d_placement;
+    p.flags = KF_STEP | KF_STORE | (a->finalize ? KF_FINALIZE : 0u);
+    if (a->time_ms > 0) p.elapsed = a->time_ms;
+    p.reset_seeds = a->d_reset_seeds;
+    p.reward = a->d_reward; p.done = a->d_done; p.lines = a->d_lines;
+    set_obs(p, a->obs);
+    CK(h->ops->launch_game(p, a->n, (cudaStream_t)stream));
+    return B2T_OK;
+}
+
+int b2t_observe(b2t_handle* h, const int32_t* d_idx, int32_t n, const b2t_obs* obs, void* stream) {
+    if (!h || !obs) return B2T_ERR_ARG;
+    if (n < 0 || n > h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_observe: bad n%s");
+    if (int r = check_obs(h, *obs)) return r;
+    CK(cudaSetDevice(h->cfg.device));
+    KParams p; base_params(h, p);
+    p.idx = d_idx; p.n = n; p.flags = 0;
+    set_obs(p, *obs);
+    CK(h->ops->launch_game(p, n, (cudaStream_t)stream));
+    return B2T_OK;
+}
+
+static int ensure_cache(b2t_handle* h) {
+    if (h->plc) return B2T_OK;
+    CK(cudaMalloc((void**)&h->plc, (size_t)h->cfg.n_games * h->ops->KMAX * h->ops->KEYW * sizeof(uint32_t)));
+    return B2T_OK;
+}
+
+int b2t_enumerate(b2t_handle* h, const int32_t* d_idx, int32_t n, const uint8_t* d_player, int32_t* d_K, uint8_t* d_keys,
+                  uint8_t* d_key_len, int32_t kmax, int32_t lmax, void* stream) {
+    if (!h) return B2T_ERR_ARG;
+    if (n < 0 || n > h->cfg.n_games || !d_player) return fail(h, B2T_ERR_ARG, "b2t_enumerate: bad n or NULL d_player%s");
+    if ((d_keys || d_key_len) && (kmax < 1 || lmax < 1)) return fail(h, B2T_ERR_ARG, "b2t_enumerate: kmax/lmax must be positive%s");
+    CK(cudaSetDevice(h->cfg.device));
+    if (int r = ensure_cache(h)) return r;
+    EParams e;
+    memset(&e, 0, sizeof e);
+    e.state = h->state; e.n_games = h->cfg.n_games; e.idx = d_idx; e.n = n; e.player = d_player;
+    e.bar_null = h->cfg.bar_null_moves ? 1 : 0; e.plc = h->plc; e.kcache = h->kcache; e.K = d_K; e.stats = h->stats; e.tabs = h->tabs;
+    CK(h->ops->launch_enum(e, (cudaStream_t)stream));
+    h->enumerated = true;
+    if (d_keys || d_key_len) CK(h->ops->launch_unpack(h->plc, h->kcache, d_idx, n, kmax, lmax, d_keys, d_key_len, (cudaStream_t)stream));
+    return B2T_OK;
+}
+
+static int scan_offsets(b2t_handle* h, const int32_t* d_K, int n, int32_t* d_offsets, cudaStream_t s) {
+    const int tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (tiles > SCAN_TILE) return fail(h, B2T_ERR_ARG, "b2t_expand: n too large for the offset scan%s");
+    scan_tile_sums<<<tiles, SCAN_TPB, 0, s>>>(d_K, n, h->scan_sums);
+    scan_sums<<<1, SCAN_TPB, 0, s>>>(h->scan_sums, tiles);
+    scan_finish<<<tiles, SCAN_TPB, 0, s>>>(d_K, n, h->scan_sums, d_offsets);
+    CK(cudaGetLastError());
+    return B2T_OK;
+}
+
+int b2t_expand(b2t_handle* h, const b2t_expand_args* a, void* stream) {
+    if (!h || !a) return B2T_ERR_ARG;
+    if (a->n < 1 || a->n > h->cfg.n_games || !a->d_player || !a->d_K || !a->d_offsets || a->capacity < 0)
+        return fail(h, B2T_ERR_ARG, "b2t_expand: need n>=1, d_player, d_K, d_offsets, capacity>=0%s");
+    if (int r = check_obs(h, a->obs)) return r;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (int r = b2t_enumerate(h, a->d_game_idx, a->n, a->d_player, a->d_K, nullptr, nullptr, 0, 0, stream)) return r;
+    if (int r = scan_offsets(h, a->d_K, a->n, a->d_offsets, s)) return r;
+    KParams p; base_params(h, p);
+    p.idx = a->d_game_idx; p.n = a->n; p.player = a->d_player;
+    p.flags = KF_EXPAND | (a->finalize ? KF_FINALIZE : 0u);
+    if (a->time_ms > 0) p.elapsed = a->time_ms;
+    p.offsets = a->d_offsets; p.capacity = a->capacity;
+    p.reward = a->d_reward; p.done = a->d_done; p.lines = a->d_lines;
+    p.board_of = a->d_board; p.keys_out = a->d_keys; p.key_len_out = a->d_key_len; p.lmax_out = a->lmax;
+    set_obs(p, a->obs);
+    CK(h->ops->launch_game(p, a->capacity, s));
+    return B2T_OK;
+}
+
+int b2t_snapshot(b2t_handle* h, int32_t slot, void* stream) {
+    if (!h || slot < 0 || slot >= B2T_SNAPSHOT_SLOTS) return fail(h, B2T_ERR_ARG, "b2t_snapshot: bad slot%s");
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->snap[slot]) CK(cudaMalloc((void**)&h->snap[slot], h->state_vecs * sizeof(uint4)));
+    CK(cudaMemcpyAsync(h->snap[slot], h->state, h->state_vecs * sizeof(uint4), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return B2T_OK;
+}
+int b2t_restore(b2t_handle* h, int32_t slot, void* stream) {
+    if (!h || slot < 0 || slot >= B2T_SNAPSHOT_SLOTS || !h->snap[slot]) return fail(h, B2T_ERR_ARG, "b2t_restore: bad or empty slot%s");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpyAsync(h->state, h->snap[slot], h->state_vecs * sizeof(uint4), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return B2T_OK;
+}
+
+int b2t_export_state(b2t_handle* h, int32_t game, void* h_buf, void* stream) {
+    if (!h || !h_buf || game < 0 || game >= h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_export_state: bad argument%s");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    gather_game_kernel<<<1, 64, 0, s>>>(h->state, h->cfg.n_games, game, h->ops->NV, h->xfer);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_buf, h->xfer, (size_t)h->ops->NV * 16, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return B2T_OK;
+}
+int b2t_import_state(b2t_handle* h, int32_t game, const void* h_buf, void* stream) {
+    if (!h || !h_buf || game < 0 || game >= h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_import_state: bad argument%s");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(h->xfer, h_buf, (size_t)h->ops->NV * 16, cudaMemcpyHostToDevice, s));
+    scatter_game_kernel<<<1, 64, 0, s>>>(h->state, h->cfg.n_games, game, h->ops->NV, h->xfer);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    return B2T_OK;
+}
+
+static int poke(b2t_handle* h, int32_t game, int32_t player, uint32_t flag, int value, void* stream) {
+    if (!h || game < 0 || game >= h->cfg.n_games || player < 0 || player > 1) return fail(h, B2T_ERR_ARG, "poke: bad game/player%s");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int32_t* d_idx = reinterpret_cast<int32_t*>(h->d_total) + 4;
+    CK(cudaMemcpyAsync(d_idx, &game, sizeof game, cudaMemcpyHostToDevice, s));
+    KParams p; base_params(h, p);
+    p.idx = d_idx; p.n = 1; p.flags = flag | KF_STORE; p.poke_player = player; p.poke_value = value;
+    CK(h->ops->launch_game(p, 1, s));
+    CK(cudaStreamSynchronize(s));
+    return B2T_OK;
+}
+int b2t_poke_dead(b2t_handle* h, int32_t game, int32_t player, int32_t dead, void* stream) { return poke(h, game, player, KF_POKE_DEAD, dead ? 1 : 0, stream); }
+int b2t_clear_field(b2t_handle* h, int32_t game, int32_t player, void* stream) { return poke(h, game, player, KF_CLEAR_FIELD, 0, stream); }
+
+int b2t_stats(b2t_handle* h, uint64_t* h_out, void* stream) {
+    if (!h || !h_out) return B2T_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    unsigned long long tmp[STAT_SLICES * STAT_WORDS];
+    CK(cudaMemcpyAsync(tmp, h->stats, sizeof tmp, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int j = 0; j < STAT_WORDS; j++) {
+        h_out[j] = 0;
+        for (int s = 0; s < STAT_SLICES; s++) h_out[j] += tmp[s * STAT_WORDS + j];
+    }
+    return B2T_OK;
+}
+
+int b2t_debug_streams(b2t_handle* h, uint32_t seed16, int32_t n, uint8_t* h_pieces, uint8_t* h_holes) {
+    if (!h || seed16 >= (uint32_t)RNG_SEEDS || n < 0) return B2T_ERR_ARG;
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t np = (size_t)(n < h->cfg.piece_stream_len ? n : h->cfg.piece_stream_len), nh = (size_t)(n < h->cfg.hole_stream_len ? n : h->cfg.hole_stream_len);
+    if (h_pieces) CK(cudaMemcpy(h_pieces, h->piece_tab + (size_t)seed16 * h->cfg.piece_stream_len, np, cudaMemcpyDeviceToHost));
+    if (h_holes) CK(cudaMemcpy(h_holes, h->hole_tab + (size_t)seed16 * h->cfg.hole_stream_len, nh, cudaMemcpyDeviceToHost));
+    return B2T_OK;
+}
+
+// ------------------------------------------------------------------------------------------ host-buffer entry points
+struct In {   // stage one optional host array into the input arena
+    size_t off = 0, bytes = 0;
+    const void* src = nullptr;
+};
+static const void* dev_in(const Arena& a, const In& i) { return i.src ? a.d + i.off : nullptr; }
+struct Out {
+    size_t off = 0, bytes = 0;
+    void* dst = nullptr;
+};
+static void* dev_out(const Arena& a, const Out& o) { return o.dst ? a.d + o.off : nullptr; }
+
+static int stage_in(b2t_handle* h, std::vector<In*> ins, cudaStream_t s) {
+    size_t total = 0;
+    for (auto i : ins) if (i->src) total += (i->bytes + 255) & ~(size_t)255;
+    CK(h->in.reserve(total + 256));
+    for (auto i : ins) if (i->src) { i->off = h->in.take(i->bytes); memcpy(h->in.h + i->off, i->src, i->bytes); }
+    if (h->in.at) CK(cudaMemcpyAsync(h->in.d, h->in.h, h->in.at, cudaMemcpyHostToDevice, s));
+    return B2T_OK;
+}
+static int plan_out(b2t_handle* h, std::vector<Out*> outs) {
+    size_t total = 0;
+    for (auto o : outs) if (o->dst) total += (o->bytes + 255) & ~(size_t)255;
+    CK(h->out.reserve(total + 256));
+    for (auto o : outs) if (o->dst) o->off = h->out.take(o->bytes);
+    return B2T_OK;
+}
+static int fetch_out(b2t_handle* h, std::vector<Out*> outs, cudaStream_t s) {
+    if (h->out.at) CK(cudaMemcpyAsync(h->out.h, h->out.d, h->out.at, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (auto o : outs) if (o->dst) memcpy(o->dst, h->out.h + o->off, o->bytes);
+    return B2T_OK;
+}
+
+int b2t_reset_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint32_t* h_seeds) {
+    if (!h) return B2T_ERR_ARG;
+    if (n < 0 || n > h->cfg.n_games || !h_seeds) return fail(h, B2T_ERR_ARG, "b2t_reset_host: bad n or NULL seeds%s");
+    CK(cudaSetDevice(h->cfg.device));
+    In idx, seeds;
+    idx.src = h_idx; idx.bytes = (size_t)n * 4; seeds.src = h_seeds; seeds.bytes = (size_t)n * 4;
+    if (int r = stage_in(h, {&idx, &seeds}, 0)) return r;
+    if (int r = b2t_reset(h, (const int32_t*)dev_in(h->in, idx), n, (const uint32_t*)dev_in(h->in, seeds), nullptr)) return r;
+    CK(cudaStreamSynchronize(0));
+    return B2T_OK;
+}
+
+int b2t_step_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint8_t* h_player, const uint8_t* h_keys, const uint8_t* h_key_len,
+                  int32_t lmax, const int32_t* h_placement, int32_t finalize, int32_t time_ms, const uint32_t* h_reset_seeds,
+                  int8_t* h_reward, uint8_t* h_done, uint8_t* h_lines, uint8_t* h_field, uint8_t* h_vec, uint8_t* h_piece_idx,
+                  int32_t* h_scalars) {
+    if (!h) return B2T_ERR_ARG;
+    if (n < 0 || n > h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_step_host: bad n%s");
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t N = (size_t)n, HW = (size_t)h->ops->H * h->ops->W;
+    In idx, pl, keys, klen, plc, rs;
+    idx.src = h_idx; idx.bytes = N * 4; pl.src = h_player; pl.bytes = N;
+    keys.src = h_keys; keys.bytes = N * (size_t)(lmax > 0 ? lmax : 0); klen.src = h_key_len; klen.bytes = N;
+    plc.src = h_placement; plc.bytes = N * 4; rs.src = h_reset_seeds; rs.bytes = N * 4;
+    if (int r = stage_in(h, {&idx, &pl, &keys, &klen, &plc, &rs}, 0)) return r;
+    Out rew, done, lines, field, vec, pidx, scal;
+    rew.dst = h_reward; rew.bytes = N; done.dst = h_done; done.bytes = N; lines.dst = h_lines; lines.bytes = 2 * N;
+    field.dst = h_field; field.bytes = 2 * HW * N; vec.dst = h_vec; vec.bytes = 2 * B2T_VEC_LEN * N;
+    pidx.dst = h_piece_idx; pidx.bytes = 2 * N; scal.dst = h_scalars; scal.bytes = 64 * N;
+    if (int r = plan_out(h, {&rew, &done, &lines, &field, &vec, &pidx, &scal})) return r;
+    b2t_step_args a;
+    memset(&a, 0, sizeof a);
+    a.d_game_idx = (const int32_t*)dev_in(h->in, idx); a.n = n; a.d_player = (const uint8_t*)dev_in(h->in, pl);
+    a.d_keys = (const uint8_t*)dev_in(h->in, keys); a.d_key_len = (const uint8_t*)dev_in(h->in, klen); a.lmax = lmax;
+    a.d_placement = (const int32_t*)dev_in(h->in, plc); a.finalize = finalize; a.time_ms = time_ms;
+    a.d_reset_seeds = (const uint32_t*)dev_in(h->in, rs);
+    a.d_reward = (int8_t*)dev_out(h->out, rew); a.d_done = (uint8_t*)dev_out(h->out, done); a.d_lines = (uint8_t*)dev_out(h->out, lines);
+    a.obs.d_field = (uint8_t*)dev_out(h->out, field); a.obs.d_vec = (uint8_t*)dev_out(h->out, vec);
+    a.obs.d_piece_idx = (uint8_t*)dev_out(h->out, pidx); a.obs.d_scalars = (int32_t*)dev_out(h->out, scal);
+    if (int r = b2t_step(h, &a, nullptr)) return r;
+    return fetch_out(h, {&rew, &done, &lines, &field, &vec, &pidx, &scal}, 0);
+}
+
+int b2t_observe_host(b2t_handle* h, const int32_t* h_idx, int32_t n, uint8_t* h_field, uint8_t* h_vec, uint8_t* h_piece_idx, int32_t* h_scalars) {
+    if (!h) return B2T_ERR_ARG;
+    if (n < 0 || n > h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_observe_host: bad n%s");
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t N = (size_t)n, HW = (size_t)h->ops->H * h->ops->W;
+    In idx; idx.src = h_idx; idx.bytes = N * 4;
+    if (int r = stage_in(h, {&idx}, 0)) return r;
+    Out field, vec, pidx, scal;
+    field.dst = h_field; field.bytes = 2 * HW * N; vec.dst = h_vec; vec.bytes = 2 * B2T_VEC_LEN * N;
+    pidx.dst = h_piece_idx; pidx.bytes = 2 * N; scal.dst = h_scalars; scal.bytes = 64 * N;
+    if (int r = plan_out(h, {&field, &vec, &pidx, &scal})) return r;
+    b2t_obs o;
+    o.d_field = (uint8_t*)dev_out(h->out, field); o.d_vec = (uint8_t*)dev_out(h->out, vec);
+    o.d_piece_idx = (uint8_t*)dev_out(h->out, pidx); o.d_scalars = (int32_t*)dev_out(h->out, scal);
+    if (int r = b2t_observe(h, (const int32_t*)dev_in(h->in, idx), n, &o, nullptr)) return r;
+    return fetch_out(h, {&field, &vec, &pidx, &scal}, 0);
+}
+
+int b2t_enumerate_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint8_t* h_player, int32_t* h_K, uint8_t* h_keys,
+                       uint8_t* h_key_len, int32_t kmax, int32_t lmax) {
+    if (!h) return B2T_ERR_ARG;
+    if (n < 0 || n > h->cfg.n_games || !h_player) return fail(h, B2T_ERR_ARG, "b2t_enumerate_host: bad n or NULL player%s");
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t N = (size_t)n;
+    In idx, pl; idx.src = h_idx; idx.bytes = N * 4; pl.src = h_player; pl.bytes = N;
+    if (int r = stage_in(h, {&idx, &pl}, 0)) return r;
+    Out K, keys, klen;
+    K.dst = h_K; K.bytes = N * 4; keys.dst = h_keys; keys.bytes = N * (size_t)kmax * (size_t)lmax; klen.dst = h_key_len; klen.bytes = N * (size_t)kmax;
+    if (int r = plan_out(h, {&K, &keys, &klen})) return r;
+    if (int r = b2t_enumerate(h, (const int32_t*)dev_in(h->in, idx), n, (const uint8_t*)dev_in(h->in, pl), (int32_t*)dev_out(h->out, K),
+                              (uint8_t*)dev_out(h->out, keys), (uint8_t*)dev_out(h->out, klen), kmax, lmax, nullptr)) return r;
+    return fetch_out(h, {&K, &keys, &klen}, 0);
+}
+
+int b2t_expand_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint8_t* h_player, int32_t finalize, int32_t time_ms,
+                    int32_t capacity, int32_t* h_K, int32_t* h_offsets, int32_t* h_total, uint8_t* h_keys, uint8_t* h_key_len, int32_t lmax,
+                    int8_t* h_reward, uint8_t* h_done, uint8_t* h_lines, uint8_t* h_field, uint8_t* h_vec, uint8_t* h_piece_idx) {
+    if (!h) return B2T_ERR_ARG;
+    if (n < 1 || n > h->cfg.n_games || !h_player || capacity < 0) return fail(h, B2T_ERR_ARG, "b2t_expand_host: bad n/capacity or NULL player%s");
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t N = (size_t)n, C = (size_t)capacity, HW = (size_t)h->ops->H * h->ops->W;
+    In idx, pl; idx.src = h_idx; idx.bytes = N * 4; pl.src = h_player; pl.bytes = N;
+    if (int r = stage_in(h, {&idx, &pl}, 0)) return r;
+    Out K, offs, keys, klen, rew, done, lines, field, vec, pidx;
+    std::vector<int32_t> k_tmp, o_tmp;
+    if (!h_K) { k_tmp.resize(N); h_K = k_tmp.data(); }
+    if (!h_offsets) { o_tmp.resize(N + 1); h_offsets = o_tmp.data(); }
+    K.dst = h_K; K.bytes = N * 4; offs.dst = h_offsets; offs.bytes = (N + 1) * 4;
+    keys.dst = h_keys; keys.bytes = C * (size_t)(lmax > 0 ? lmax : 0); klen.dst = h_key_len; klen.bytes = C;
+    rew.dst = h_reward; rew.bytes = C; done.dst = h_done; done.bytes = C; lines.dst = h_lines; lines.bytes = 2 * C;
+    field.dst = h_field; field.bytes = 2 * HW * C; vec.dst = h_vec; vec.bytes = 2 * B2T_VEC_LEN * C; pidx.dst = h_piece_idx; pidx.bytes = 2 * C;
+    if (int r = plan_out(h, {&K, &offs, &keys, &klen, &rew, &done, &lines, &field, &vec, &pidx})) return r;
+    b2t_expand_args a;
+    memset(&a, 0, sizeof a);
+    a.d_game_idx = (const int32_t*)dev_in(h->in, idx); a.n = n; a.d_player = (const uint8_t*)dev_in(h->in, pl);
+    a.finalize = finalize; a.time_ms = time_ms; a.capacity = capacity;
+    a.d_K = (int32_t*)dev_out(h->out, K); a.d_offsets = (int32_t*)dev_out(h->out, offs);
+    a.d_keys = (uint8_t*)dev_out(h->out, keys); a.d_key_len = (uint8_t*)dev_out(h->out, klen); a.lmax = lmax;
+    a.d_reward = (int8_t*)dev_out(h->out, rew); a.d_done = (uint8_t*)dev_out(h->out, done); a.d_lines = (uint8_t*)dev_out(h->out, lines);
+    a.obs.d_field = (uint8_t*)dev_out(h->out, field); a.obs.d_vec = (uint8_t*)dev_out(h->out, vec); a.obs.d_piece_idx = (uint8_t*)dev_out(h->out, pidx);
+    if (int r = b2t_expand(h, &a, nullptr)) return r;
+    if (int r = fetch_out(h, {&K, &offs, &keys, &klen, &rew, &done, &lines, &field, &vec, &pidx}, 0)) return r;
+    if (h_total) *h_total = h_offsets[n];
+    return B2T_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,617 @@
+// b200tetris — sm_100a kernels.  One thread = one game (reset / step / observe) or one simulated placement (expand);
+// boards in shared memory (thread-private columns, stride = block size, so every access is bank-conflict free),
+// scalars in registers, HBM traffic = coalesced 128-bit state vectors in, state + uint8 observation tensors out.
+// The observation bytes are produced by a warp-cooperative pass: the 32 rows' bit streams are packed back to back
+// in shared memory and every lane expands 16 bits -> one 128-bit store, so the [rows,2,H,W] tensor is written fully
+// coalesced no matter how H*W aligns.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "b2t_game.cuh"
+#include "b2t_rng.cuh"
+
+namespace b2t {
+
+constexpr int TPB = 128;
+constexpr int WARPS = TPB / 32;
+constexpr int STAT_SLICES = 64;
+constexpr int STAT_WORDS = 8;
+
+struct DevTabs {
+    const uint8_t* piece;
+    const uint8_t* hole;
+    const double* powtab;
+    uint32_t piece_len, hole_len, spawn_rots;
+    uint16_t pcn[28], pcc[28];
+};
+
+enum : uint32_t {
+    KF_RESET = 1u,      // reset listed games with p.seeds before anything else
+    KF_STEP = 2u,       // perform_action
+    KF_FINALIZE = 4u,   // ... including finish_action
+    KF_STORE = 8u,      // write the state back
+    KF_EXPAND = 16u,    // rows are placements (offsets/placement cache), never stores
+    KF_POKE_DEAD = 32u, // state.lock()-style write: p.poke_player / p.poke_value
+    KF_CLEAR_FIELD = 64u
+};
+
+struct KParams {
+    uint4* state;
+    int32_t n_games;
+    const int32_t* idx;
+    int32_t n;
+    uint32_t flags;
+    const uint32_t* seeds;        // KF_RESET
+    const uint8_t* player;        // KF_STEP / KF_EXPAND
+    const uint8_t* keys;
+    const uint8_t* key_len;
+    int32_t lmax;
+    const int32_t* placement;
+    const uint32_t* plc;          // placement cache [n_games][KMAX][KEYW]
+    const int32_t* kcache;        // [n_games]
+    int32_t elapsed;
+    const uint32_t* reset_seeds;  // fused reset of finished games
+    const int32_t* offsets;       // KF_EXPAND: [n+1]
+    int32_t capacity;
+    int32_t poke_player, poke_value;
+    // outputs (row-indexed)
+    int8_t* reward;
+    uint8_t* done;
+    uint8_t* lines;
+    uint8_t* field;
+    uint8_t* vec;
+    uint8_t* piece_idx;
+    int32_t* scalars;
+    int32_t* board_of;            // KF_EXPAND
+    uint8_t* keys_out;
+    uint8_t* key_len_out;
+    int32_t lmax_out;
+    unsigned long long* stats;    // [STAT_SLICES][STAT_WORDS]
+    DevTabs tabs;
+};
+
+template <class G> struct SmemLayout {
+    typedef typename G::col_t col_t;
+    static constexpr int HW = G::H * G::W;
+    static constexpr int WB = 2 * HW;                         // words of packed field bits per warp (32 rows x 2HW bits)
+    static constexpr int COLS = 2 * G::NCOL * TPB * (int)sizeof(col_t);
+    static constexpr int STREAM = 2 * G::SW * TPB * 4;
+    static constexpr int BITS = WARPS * (WB + 1) * 4;
+    static constexpr int VEC = WARPS * 32 * 2 * VEC_LEN;
+    static constexpr int TAB = 64 * 2;
+    static constexpr int GAME_TOTAL = COLS + STREAM + BITS + ((VEC + 15) / 16) * 16 + TAB;
+    static constexpr int ENUM_TOTAL = G::NCOL * TPB * (int)sizeof(col_t) + TAB;
+};
+
+// ---------------------------------------------------------------------------------------------- cooperative outputs
+// wb: this warp's WB(+1) words.  Rows = lanes.  out = address of the warp's first row.
+template <class G>
+__device__ __forceinline__ void emit_fields(uint32_t* wb, const Board<G, TPB>& b0, const Board<G, TPB>& b1, bool has_row,
+                                            uint8_t* out, int valid_rows, int lane) {
+    constexpr int HW = G::H * G::W;
+    constexpr int WB = 2 * HW;
+    for (int w = lane; w < WB + 1; w += 32) wb[w] = 0u;
+    __syncwarp();
+    if (has_row) {
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++) {
+            const Board<G, TPB>& b = pl ? b1 : b0;
+#pragma unroll
+            for (int w = 0; w < G::SW; w++) {
+                const uint32_t v = b.sw(w);
+                const int o = lane * 2 * HW + pl * HW + 32 * w;
+                if ((HW & 31) == 0) {
+                    wb[o >> 5] = v;
+                } else if (v) {
+                    const int sh = o & 31;
+                    atomicOr(&wb[o >> 5], v << sh);
+                    if (sh) atomicOr(&wb[(o >> 5) + 1], v >> (32 - sh));
+                }
+            }
+        }
+    }
+    __syncwarp();
+    const int valid_bytes = valid_rows * 2 * HW;
+    const uint16_t* hb = reinterpret_cast<const uint16_t*>(wb);
+    constexpr int NCH = 4 * HW;  // 16-byte chunks in 32 rows
+    for (int c = lane; c < NCH; c += 32) {
+        const int byte0 = 16 * c;
+        if (byte0 >= valid_bytes) break;
+        const uint32_t h = hb[c];
+        uint4 q;
+        q.x = ((h & 15u) * 0x00204081u) & 0x01010101u;
+        q.y = (((h >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+        q.z = (((h >> 8) & 15u) * 0x00204081u) & 0x01010101u;
+        q.w = (((h >> 12) & 15u) * 0x00204081u) & 0x01010101u;
+        if (byte0 + 16 <= valid_bytes) {
+            *reinterpret_cast<uint4*>(out + byte0) = q;
+        } else {
+            const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+            for (int k = 0; byte0 + k < valid_bytes; k++) out[byte0 + k] = (uint8_t)(qq[k >> 2] >> (8 * (k & 3)));
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void emit_vecs(uint8_t* sv, const PS& p0, const PS& p1, bool has_row, uint8_t* out, int valid_rows, int lane) {
+    if (has_row) {
+        uint8_t v[VEC_LEN];
+        observe_vec(p0, v);
+#pragma unroll
+        for (int k = 0; k < VEC_LEN; k++) sv[lane * 2 * VEC_LEN + k] = v[k];
+        observe_vec(p1, v);
+#pragma unroll
+        for (int k = 0; k < VEC_LEN; k++) sv[lane * 2 * VEC_LEN + VEC_LEN + k] = v[k];
+    }
+    __syncwarp();
+    const uint16_t* s16 = reinterpret_cast<const uint16_t*>(sv);
+    uint16_t* o16 = reinterpret_cast<uint16_t*>(out);
+    const int valid = valid_rows * VEC_LEN;  // halfwords
+    for (int k = lane; k < valid; k += 32) o16[k] = s16[k];
+    __syncwarp();
+}
+
+// 16 u8 key codes -> 16 packed 4-bit tokens (codes > 10 become the no-op 0, PythonHandle.cpp:109-110)
+__device__ __forceinline__ uint32_t squeeze_keys(uint32_t w) {
+    w &= ~__vcmpgtu4(w, 0x0A0A0A0Au);
+    uint32_t x = w & 0x0F0F0F0Fu;
+    x = (x | (x >> 4)) & 0x00FF00FFu;
+    x = (x | (x >> 8)) & 0x0000FFFFu;
+    return x;
+}
+
+// ---------------------------------------------------------------------------------------------- the game kernel
+template <class G>
+__global__ void __launch_bounds__(TPB) game_kernel(const KParams p) {
+    typedef typename G::col_t col_t;
+    typedef SmemLayout<G> L;
+    constexpr int KW = G::KEYW;
+    extern __shared__ __align__(16) unsigned char smem[];
+    col_t* s_cols = reinterpret_cast<col_t*>(smem);
+    uint32_t* s_stream = reinterpret_cast<uint32_t*>(smem + L::COLS);
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem + L::COLS + L::STREAM);
+    uint8_t* s_vec = smem + L::COLS + L::STREAM + L::BITS;
+    uint16_t* s_tab = reinterpret_cast<uint16_t*>(smem + L::COLS + L::STREAM + L::BITS + ((L::VEC + 15) / 16) * 16);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row = blockIdx.x * TPB + tid;
+    if (tid < 28) { s_tab[tid] = p.tabs.pcn[tid]; s_tab[32 + tid] = p.tabs.pcc[tid]; }
+    Tabs tb;
+    tb.pcn = s_tab; tb.pcc = s_tab + 32;
+    tb.piece = p.tabs.piece; tb.hole = p.tabs.hole; tb.powtab = p.tabs.powtab;
+    tb.piece_len = p.tabs.piece_len; tb.hole_len = p.tabs.hole_len; tb.spawn_rots = p.tabs.spawn_rots;
+
+    Game<G, TPB> g;
+#pragma unroll
+    for (int pl = 0; pl < 2; pl++) {
+        g.b[pl].cols = s_cols + pl * G::NCOL * TPB + tid;
+        g.b[pl].stream = s_stream + pl * G::SW * TPB + tid;
+        board_init_walls<G, TPB>(g.b[pl]);
+    }
+    __syncthreads();
+
+    const bool expand = (p.flags & KF_EXPAND) != 0;
+    int total_rows = p.n, i = row, k = 0;
+    if (expand) {
+        total_rows = p.offsets[p.n];
+        if (total_rows > p.capacity) total_rows = p.capacity;
+        if (row < total_rows) {
+            int lo = 0, hi = p.n;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (p.offsets[mid] <= row) lo = mid; else hi = mid;
+            }
+            i = lo;
+            k = row - p.offsets[lo];
+        }
+    }
+    const bool active = row < total_rows;
+    // per-thread stat contributions
+    int st_steps = 0, st_done = 0, st_w0 = 0, st_w1 = 0, st_both = 0, st_lines = 0, st_gq = 0, st_rng = 0;
+
+    if (active) {
+        const int gi = p.idx ? p.idx[i] : i;
+        {
+            const uint4* src = p.state + gi;
+#pragma unroll
+            for (int v = 0; v < G::NV; v++) {
+                const uint4 q = src[(size_t)v * (size_t)p.n_games];
+                game_put_word(g, 4 * v + 0, q.x);
+                game_put_word(g, 4 * v + 1, q.y);
+                game_put_word(g, 4 * v + 2, q.z);
+                game_put_word(g, 4 * v + 3, q.w);
+            }
+        }
+        game_unpack(g);
+        const int flags_before = g.p[0].flags | g.p[1].flags;
+        if (p.flags & KF_RESET) game_reset(g, tb, p.seeds[i]);
+        if (p.flags & KF_POKE_DEAD) {
+            if (p.poke_player == 0) g.p[0].dead = p.poke_value; else g.p[1].dead = p.poke_value;
+        }
+        if (p.flags & KF_CLEAR_FIELD) board_clear<G, TPB>(p.poke_player ? g.b[1] : g.b[0]);
+        if (p.flags & (KF_STEP | KF_EXPAND)) {
+            const int player = p.player[i] ? 1 : 0;
+            uint32_t kw[KW];
+            int nkeys;
+            if (expand || p.placement) {
+                int sel = expand ? k : p.placement[i];
+                const int kc = p.kcache[gi];
+                const bool valid = sel >= 0 && sel < kc && sel < G::KMAX;   // out of range -> null action (action_list.py:27-33)
+                const uint4* src = reinterpret_cast<const uint4*>(p.plc + ((size_t)gi * G::KMAX + (valid ? sel : 0)) * KW);
+#pragma unroll
+                for (int j = 0; j < KW / 4; j++) {
+                    const uint4 q = src[j];
+                    kw[4 * j] = valid ? q.x : 0u; kw[4 * j + 1] = valid ? q.y : 0u;
+                    kw[4 * j + 2] = valid ? q.z : 0u; kw[4 * j + 3] = valid ? q.w : 0u;
+                }
+                nkeys = packed_len<KW>(kw);
+            } else {
+                nkeys = p.key_len[i];
+                if (nkeys > KW * 8) nkeys = KW * 8;
+                if (nkeys > p.lmax) nkeys = p.lmax;
+                const uint8_t* kp = p.keys + (size_t)i * (size_t)p.lmax;
+                if ((p.lmax & 15) == 0 && ((reinterpret_cast<uintptr_t>(p.keys) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < KW; j++) kw[j] = 0u;
+#pragma unroll
+                    for (int j = 0; j < KW / 2; j++) {       // 16 keys per uint4 -> two packed words
+                        if (16 * j < nkeys) {
+                            const uint4 q = *reinterpret_cast<const uint4*>(kp + 16 * j);
+                            kw[2 * j] = squeeze_keys(q.x) | (squeeze_keys(q.y) << 16);
+                            kw[2 * j + 1] = squeeze_keys(q.z) | (squeeze_keys(q.w) << 16);
+                        }
+                    }
+                } else {
+                    pack_keys<KW>(kp, nkeys, kw);
+                }
+            }
+            const bool was_over = (g.gf() & GF_ROUND_OVER) != 0;
+            const bool finalize = (p.flags & KF_FINALIZE) != 0;
+            int rew;
+            const bool done = game_perform<G, TPB, KW>(g, tb, player, kw, nkeys, finalize, p.elapsed, &rew);
+            if (p.reward) p.reward[row] = (int8_t)rew;
+            if (p.done) p.done[row] = done ? 1 : 0;
+            if (p.lines) *reinterpret_cast<uint16_t*>(p.lines + 2 * (size_t)row) = (uint16_t)((g.p[0].reward & 255) | ((g.p[1].reward & 255) << 8));
+            if (expand) {
+                if (p.board_of) p.board_of[row] = i;
+                if (p.key_len_out) p.key_len_out[row] = (uint8_t)nkeys;
+                if (p.keys_out) {
+                    uint8_t* ko = p.keys_out + (size_t)row * (size_t)p.lmax_out;
+                    for (int j = 0; j < p.lmax_out; j++) ko[j] = (j < KW * 8) ? (uint8_t)((kw[j >> 3] >> (4 * (j & 7))) & 15u) : 0;
+                }
+            } else if (finalize && !was_over) {
+                st_steps = 1;
+                st_lines = g.p[0].reward + g.p[1].reward;
+                if (done) {
+                    st_done = 1;
+                    const int d0 = g.p[0].dead, d1 = g.p[1].dead;
+                    st_both = d0 && d1; st_w0 = !d0 && d1; st_w1 = d0 && !d1;
+                }
+            }
+            if (!expand && done && p.reset_seeds) game_reset(g, tb, p.reset_seeds[i]);
+        }
+        const int flags_after = g.p[0].flags | g.p[1].flags;
+        st_gq = ((flags_after & ~flags_before) & 1) != 0;
+        st_rng = ((flags_after & ~flags_before) & 2) != 0;
+        if ((p.flags & KF_STORE) && !expand) {
+            game_pack(g);
+            uint4* dst = p.state + gi;
+#pragma unroll
+            for (int v = 0; v < G::NV; v++) {
+                uint4 q;
+                q.x = game_get_word(g, 4 * v + 0);
+                q.y = game_get_word(g, 4 * v + 1);
+                q.z = game_get_word(g, 4 * v + 2);
+                q.w = game_get_word(g, 4 * v + 3);
+                dst[(size_t)v * (size_t)p.n_games] = q;
+            }
+        }
+        if (p.piece_idx) *reinterpret_cast<uint16_t*>(p.piece_idx + 2 * (size_t)row) = (uint16_t)((g.p[0].kind & 255) | ((g.p[1].kind & 255) << 8));
+        if (p.scalars) {
+            int32_t* s = p.scalars + (size_t)row * 16;
+#pragma unroll
+            for (int pl = 0; pl < 2; pl++) {
+                const PS& q = g.p[pl];
+                int4 a = make_int4(q.x, q.y, q.inc_count, q.remaining), b = make_int4(q.combo_count, q.next, q.reward, q.dead);
+                reinterpret_cast<int4*>(s)[2 * pl] = a;
+                reinterpret_cast<int4*>(s)[2 * pl + 1] = b;
+            }
+        }
+    }
+    // ---- warp-cooperative observation tensors
+    const int warp_row0 = blockIdx.x * TPB + warp * 32;
+    int valid_rows = total_rows - warp_row0;
+    valid_rows = valid_rows < 0 ? 0 : (valid_rows > 32 ? 32 : valid_rows);
+    if (p.field && valid_rows > 0)
+        emit_fields<G>(s_bits + warp * (L::WB + 1), g.b[0], g.b[1], active, p.field + (size_t)warp_row0 * (size_t)(2 * L::HW), valid_rows, lane);
+    if (p.vec && valid_rows > 0)
+        emit_vecs(s_vec + warp * 32 * 2 * VEC_LEN, g.p[0], g.p[1], active, p.vec + (size_t)warp_row0 * (size_t)(2 * VEC_LEN), valid_rows, lane);
+    // ---- episode statistics: one atomic per non-zero counter per warp, spread over slices
+    if (p.stats && (p.flags & KF_STEP)) {
+        int vals[STAT_WORDS] = {st_steps, st_done, st_w0, st_w1, st_both, st_lines, st_gq, st_rng};
+#pragma unroll
+        for (int j = 0; j < STAT_WORDS; j++) {
+            const int s = __reduce_add_sync(0xFFFFFFFFu, vals[j]);
+            if (lane == 0 && s) atomicAdd(&p.stats[(blockIdx.x % STAT_SLICES) * STAT_WORDS + j], (unsigned long long)s);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- enumerate
+struct EParams {
+    const uint4* state;
+    int32_t n_games;
+    const int32_t* idx;
+    int32_t n;
+    const uint8_t* player;
+    int32_t bar_null;
+    uint32_t* plc;      // [n_games][KMAX][KEYW]
+    int32_t* kcache;    // [n_games]
+    int32_t* K;         // [n] (may be NULL)
+    unsigned long long* stats;
+    DevTabs tabs;
+};
+
+template <int KW> struct DevSink {
+    uint32_t* out;
+    int cap, count, bad, first_fin;
+    __device__ __forceinline__ void put(int slot, const Seq<KW>& s) {
+        uint4* o = reinterpret_cast<uint4*>(out + (size_t)slot * KW);
+#pragma unroll
+        for (int j = 0; j < KW / 4; j++) o[j] = make_uint4(s.w[4 * j], s.w[4 * j + 1], s.w[4 * j + 2], s.w[4 * j + 3]);
+    }
+    __device__ __forceinline__ void top(const Seq<KW>& s, bool b) {
+        if (b) bad = 1;
+        if (count < cap) put(count, s); else bad = 1;
+        count++;
+    }
+    __device__ __forceinline__ void finesse(const Seq<KW>& s, bool b) {
+        // action_list.py:14 — first occurrence wins.  Only under-overhang sequences can repeat each other
+        // (a top drop never contains a 5/6 or a late rotation), so compare from the first finesse entry on.
+        if (first_fin >= 0) {
+            const int lim = count < cap ? count : cap;
+            for (int k = first_fin; k < lim; k++) {
+                const uint4* o = reinterpret_cast<const uint4*>(out + (size_t)k * KW);
+                bool eq = true;
+#pragma unroll
+                for (int j = 0; j < KW / 4; j++) {
+                    const uint4 q = o[j];
+                    eq = eq && q.x == s.w[4 * j] && q.y == s.w[4 * j + 1] && q.z == s.w[4 * j + 2] && q.w == s.w[4 * j + 3];
+                }
+                if (eq) return;
+            }
+        } else first_fin = count;
+        top(s, b);
+    }
+};
+
+template <class G>
+__global__ void __launch_bounds__(TPB) enumerate_kernel(const EParams p) {
+    typedef typename G::col_t col_t;
+    constexpr int KW = G::KEYW;
+    extern __shared__ __align__(16) unsigned char smem[];
+    col_t* s_cols = reinterpret_cast<col_t*>(smem);
+    uint16_t* s_tab = reinterpret_cast<uint16_t*>(smem + G::NCOL * TPB * sizeof(col_t));
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x * TPB + tid;
+    if (tid < 28) { s_tab[tid] = p.tabs.pcn[tid]; s_tab[32 + tid] = p.tabs.pcc[tid]; }
+    Tabs tb;
+    tb.pcn = s_tab; tb.pcc = s_tab + 32;
+    tb.piece = p.tabs.piece; tb.hole = p.tabs.hole; tb.powtab = p.tabs.powtab;
+    tb.piece_len = p.tabs.piece_len; tb.hole_len = p.tabs.hole_len; tb.spawn_rots = p.tabs.spawn_rots;
+    Board<G, TPB> b;
+    b.cols = s_cols + tid;
+    b.stream = nullptr;
+    board_init_walls<G, TPB>(b);
+    __syncthreads();
+    if (i >= p.n) return;
+    const int gi = p.idx ? p.idx[i] : i;
+    const int pl = p.player[i] ? 1 : 0;
+    const uint32_t* words = reinterpret_cast<const uint32_t*>(p.state);
+    auto word = [&](int wi) { return words[((size_t)(wi >> 2) * (size_t)p.n_games + (size_t)gi) * 4 + (wi & 3)]; };
+    const int base = pl * G::PW;
+    for (int c = 0; c < G::W; c++) {
+        if (G::CW == 1) b.col(c) = (col_t)word(base + c);
+        else b.col(c) = (col_t)((uint64_t)word(base + 2 * c) | ((uint64_t)word(base + 2 * c + 1) << 32));
+    }
+    const uint32_t w0 = word(base + G::W * G::CW + G::SW);
+    const int kind = w0 & 7, rot = (w0 >> 3) & 3;
+    DevSink<KW> sink;
+    const int off = p.bar_null ? 0 : 1;
+    uint32_t* lst = p.plc + (size_t)gi * G::KMAX * KW;
+    sink.out = lst + off * KW; sink.cap = G::KMAX - off; sink.count = 0; sink.bad = 0; sink.first_fin = -1;
+    if (kind <= 6) {
+        Enumerator<G, TPB, KW, DevSink<KW>> e(b, tb, kind, sink);
+        e.run(rot);
+    }
+    int K = sink.count + off;
+    if (sink.count == 0 || off) {   // null action [0] in slot 0 (action_list.py:6-12,18-20)
+        Seq<KW> z; z.clear();
+        sink.out = lst; sink.put(0, z);
+        if (sink.count == 0) K = 1;
+    }
+    p.kcache[gi] = K;
+    if (p.K) p.K[i] = K;
+    if (sink.bad && p.stats) atomicAdd(&p.stats[(blockIdx.x % STAT_SLICES) * STAT_WORDS + 7], 1ull);  // list/sequence capacity exceeded
+}
+
+// packed cache -> the u8 [n,kmax,lmax] / [n,kmax] arrays of the reference-shaped API
+template <class G>
+__global__ void unpack_keys_kernel(const uint32_t* plc, const int32_t* kcache, const int32_t* idx, int n, int kmax, int lmax,
+                                   uint8_t* keys, uint8_t* key_len) {
+    constexpr int KW = G::KEYW;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n * kmax) return;
+    const int i = (int)(t / kmax), k = (int)(t % kmax);
+    const int gi = idx ? idx[i] : i;
+    const int K = kcache[gi];
+    uint32_t w[KW];
+    const bool valid = k < K && k < G::KMAX;
+    for (int j = 0; j < KW; j++) w[j] = valid ? plc[((size_t)gi * G::KMAX + k) * KW + j] : 0u;
+    const int len = valid ? packed_len<KW>(w) : 0;
+    if (key_len) key_len[t] = (uint8_t)(len < lmax ? len : lmax);
+    if (keys)
+        for (int j = 0; j < lmax; j++) keys[(size_t)t * lmax + j] = (j < KW * 8) ? (uint8_t)((w[j >> 3] >> (4 * (j & 7))) & 15u) : 0;
+}
+
+#ifdef B2T_COMMON_KERNELS   // geometry-independent kernels live in the API translation unit only
+// ---------------------------------------------------------------------------------------------- exclusive scan of K
+constexpr int SCAN_TPB = 1024, SCAN_ITEMS = 4, SCAN_TILE = SCAN_TPB * SCAN_ITEMS;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* s_warp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, w, d);
+            if (lane >= d) w += t;
+        }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int base = warp ? s_warp[warp - 1] : 0;
+    *total = s_warp[31];
+    __syncthreads();
+    return base + inc - v;
+}
+// phase 1: per-tile sums
+__global__ void __launch_bounds__(SCAN_TPB) scan_tile_sums(const int32_t* K, int n, int32_t* sums) {
+    __shared__ int s_warp[32];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int v = 0;
+    for (int j = 0; j < SCAN_ITEMS; j++) if (base + j < n) v += K[base + j];
+    int total;
+    block_exclusive_scan(v, &total, s_warp);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+// phase 2: scan of the tile sums by one block (tiles <= SCAN_TILE, i.e. n <= 16.7M)
+__global__ void __launch_bounds__(SCAN_TPB) scan_sums(int32_t* sums, int tiles) {
+    __shared__ int s_warp[32];
+    const int base = threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS], t = 0;
+    for (int j = 0; j < SCAN_ITEMS; j++) { v[j] = (base + j < tiles) ? sums[base + j] : 0; t += v[j]; }
+    int total;
+    int ex = block_exclusive_scan(t, &total, s_warp);
+    for (int j = 0; j < SCAN_ITEMS; j++) { if (base + j < tiles) sums[base + j] = ex; ex += v[j]; }
+}
+// phase 3: offsets
+__global__ void __launch_bounds__(SCAN_TPB) scan_finish(const int32_t* K, int n, const int32_t* sums, int32_t* offsets) {
+    __shared__ int s_warp[32];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS], t = 0;
+    for (int j = 0; j < SCAN_ITEMS; j++) { v[j] = (base + j < n) ? K[base + j] : 0; t += v[j]; }
+    int total;
+    int ex = block_exclusive_scan(t, &total, s_warp) + sums[blockIdx.x];
+    for (int j = 0; j < SCAN_ITEMS; j++) {
+        if (base + j < n) offsets[base + j] = ex;
+        ex += v[j];
+        if (base + j == n - 1) offsets[n] = ex;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- tables, init, misc
+struct PieceMap { uint8_t m[8]; };
+__global__ void __launch_bounds__(64) fill_tables_kernel(uint8_t* piece, uint32_t plen, uint8_t* hole, uint32_t hlen, PieceMap map,
+                                                         int only_zs, int width) {
+    const uint32_t seed = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seed >= (uint32_t)RNG_SEEDS) return;
+    MT19937 mt;
+    fill_stream_row(mt, seed, map.m, only_zs != 0, width, piece + (size_t)seed * plen, plen, hole + (size_t)seed * hlen, hlen);
+}
+
+#endif  // B2T_COMMON_KERNELS
+
+template <class G>
+__global__ void __launch_bounds__(TPB) init_kernel(uint4* state, int n_games) {
+    typedef typename G::col_t col_t;
+    extern __shared__ __align__(16) unsigned char smem[];
+    col_t* s_cols = reinterpret_cast<col_t*>(smem);
+    uint32_t* s_stream = reinterpret_cast<uint32_t*>(smem + SmemLayout<G>::COLS);
+    const int tid = threadIdx.x, gi = blockIdx.x * TPB + tid;
+    Game<G, TPB> g;
+    for (int pl = 0; pl < 2; pl++) {
+        g.b[pl].cols = s_cols + pl * G::NCOL * TPB + tid;
+        g.b[pl].stream = s_stream + pl * G::SW * TPB + tid;
+    }
+    if (gi >= n_games) return;
+    game_init(g);
+    game_pack(g);
+#pragma unroll
+    for (int v = 0; v < G::NV; v++) {
+        uint4 q;
+        q.x = game_get_word(g, 4 * v + 0); q.y = game_get_word(g, 4 * v + 1);
+        q.z = game_get_word(g, 4 * v + 2); q.w = game_get_word(g, 4 * v + 3);
+        state[(size_t)v * (size_t)n_games + gi] = q;
+    }
+}
+
+#ifdef B2T_COMMON_KERNELS
+// export/import one game's NV vectors <-> contiguous buffer
+__global__ void gather_game_kernel(const uint4* state, int n_games, int game, int nv, uint4* out) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < nv) out[v] = state[(size_t)v * n_games + game];
+}
+__global__ void scatter_game_kernel(uint4* state, int n_games, int game, int nv, const uint4* in) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < nv) state[(size_t)v * n_games + game] = in[v];
+}
+
+#endif  // B2T_COMMON_KERNELS
+
+// ---------------------------------------------------------------------------------------------- per-geometry launch table
+struct GeomOps {
+    int H, W, NV, KMAX, KEYW, LMAX, smem_game, smem_enum;
+    cudaError_t (*prepare)();
+    cudaError_t (*launch_game)(const KParams&, int rows, cudaStream_t);
+    cudaError_t (*launch_enum)(const EParams&, cudaStream_t);
+    cudaError_t (*launch_unpack)(const uint32_t*, const int32_t*, const int32_t*, int, int, int, uint8_t*, uint8_t*, cudaStream_t);
+    cudaError_t (*launch_init)(uint4*, int, cudaStream_t);
+};
+
+template <class G> struct Launch {
+    typedef SmemLayout<G> L;
+    static cudaError_t prepare() {
+        cudaError_t e = cudaFuncSetAttribute(game_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::GAME_TOTAL);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(enumerate_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::ENUM_TOTAL);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(init_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::COLS + L::STREAM);
+    }
+    static cudaError_t game(const KParams& p, int rows, cudaStream_t s) {
+        if (rows <= 0) return cudaSuccess;
+        game_kernel<G><<<(rows + TPB - 1) / TPB, TPB, L::GAME_TOTAL, s>>>(p);
+        return cudaGetLastError();
+    }
+    static cudaError_t enumerate(const EParams& p, cudaStream_t s) {
+        if (p.n <= 0) return cudaSuccess;
+        enumerate_kernel<G><<<(p.n + TPB - 1) / TPB, TPB, L::ENUM_TOTAL, s>>>(p);
+        return cudaGetLastError();
+    }
+    static cudaError_t unpack(const uint32_t* plc, const int32_t* kc, const int32_t* idx, int n, int kmax, int lmax, uint8_t* keys,
+                              uint8_t* key_len, cudaStream_t s) {
+        const long long t = (long long)n * kmax;
+        if (t <= 0) return cudaSuccess;
+        unpack_keys_kernel<G><<<(unsigned)((t + 255) / 256), 256, 0, s>>>(plc, kc, idx, n, kmax, lmax, keys, key_len);
+        return cudaGetLastError();
+    }
+    static cudaError_t init(uint4* state, int n, cudaStream_t s) {
+        init_kernel<G><<<(n + TPB - 1) / TPB, TPB, L::COLS + L::STREAM, s>>>(state, n);
+        return cudaGetLastError();
+    }
+    static const GeomOps* ops() {
+        static const GeomOps o = {G::H, G::W, G::NV, G::KMAX, G::KEYW, G::LMAX, L::GAME_TOTAL, L::ENUM_TOTAL,
+                                  &prepare, &game, &enumerate, &unpack, &init};
+        return &o;
+    }
+};
+
+}  // namespace b2t

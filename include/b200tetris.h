@@ -1,0 +1,181 @@
+/* b200tetris — C ABI of the B200-native batched Tetris engine.
+ *
+ * Drop-in boundary for DRL-Tetris' `environment/game_backend` (pybind11 module `tetris_env`) as driven by
+ * `environment/tetris_environment_vector.py`.  One handle = a vector of independent 2-player games resident in the
+ * HBM of one GPU; every call launches hand-written sm_100a kernels on the caller's stream.  Citations below are
+ * file:line under the reference tree (/root/reference).
+ *
+ * Conventions
+ *   - every function returns B2T_OK (0) or a negative b2t_status; b2t_last_error() gives the text; nothing throws.
+ *   - pointers named d_* are DEVICE pointers on the handle's device, 16-byte aligned; pointers named h_* are HOST
+ *     pointers.  The library never takes ownership of caller memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Device-pointer calls are asynchronous;
+ *     *_host calls synchronise before returning.
+ *   - game_idx == NULL means "games 0..n-1"; otherwise n distinct game ids (duplicates in one call are undefined,
+ *     like stepping one PythonHandle from two threads).
+ *   - a handle is not thread-safe (neither is the reference); handles on different devices are independent.
+ *   - there is NO CPU fallback: without a CUDA device b2t_create fails with B2T_ERR_CUDA.
+ */
+#ifndef B200TETRIS_H
+#define B200TETRIS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2T_ABI_VERSION 1
+#define B2T_VEC_LEN 19  /* x,y,incoming_lines,combo_time,combo_count,nextpiece[7],piece[7]  (state_processors.py:33-41) */
+#define B2T_SNAPSHOT_SLOTS 4
+
+typedef enum {
+    B2T_OK = 0,
+    B2T_ERR_ARG = -1,          /* bad argument (NULL, range, alignment) */
+    B2T_ERR_UNSUPPORTED = -2,  /* field size not instantiated (csrc/b2t_geoms.h) or n_players != 2 */
+    B2T_ERR_CUDA = -3,         /* CUDA runtime error (no device, launch failure, out of memory) */
+    B2T_ERR_CAPACITY = -4,     /* caller buffer too small for the result */
+    B2T_ERR_STATE = -5         /* call order (e.g. step by placement index without a prior enumerate) */
+} b2t_status;
+
+/* Settings of tetris_environment (experiments/presets.py:123-182 "default") that reach the backend. */
+typedef struct {
+    int32_t n_games;             /* n_envs of tetris_environment_vector (tetris_environment_vector.py:10-17) */
+    int32_t n_players;           /* settings["n_players"]; only 2 is built */
+    int32_t height, width;       /* settings["game_size"] = [H, W] (PythonHandle.cpp:5-8) */
+    uint8_t piece_map[7];        /* (settings["pieces"]*7)[:7]  (tetris_environment.py:191-193 -> set_pieces) */
+    uint8_t bar_null_moves;      /* settings["bar_null_moves"] (action_list remove_null) */
+    int32_t time_ms_per_action;  /* settings["time_elapsed_each_action"], 400 */
+    int32_t piece_stream_len;    /* draws tabulated per seed (0 = default 4096); a game drawing more raises a flag */
+    int32_t hole_stream_len;     /* garbage holes tabulated per seed (0 = default 512) */
+    int32_t device;              /* CUDA device ordinal */
+    uint32_t flags;              /* reserved, 0 */
+} b2t_config;
+
+typedef struct b2t_handle b2t_handle;
+
+/* geometry-derived constants of a handle */
+typedef struct {
+    int32_t kmax;           /* capacity of a placement list */
+    int32_t lmax;           /* capacity of a key sequence */
+    int32_t state_bytes;    /* bytes of packed state per game in HBM */
+    int32_t obs_bytes;      /* 2*(H*W + 19 + 1) */
+} b2t_info;
+
+/* tetris_env.set_pieces + tetris_env.PythonHandle(n_players,[H,W]) x n_games (tetris_environment.py:34-39).
+ * Games start un-reset (no piece); call b2t_reset before stepping, as tetris_environment.__init__ does (:41). */
+int b2t_create(const b2t_config *cfg, b2t_handle **out);
+int b2t_destroy(b2t_handle *h);
+const char *b2t_last_error(const b2t_handle *h); /* h may be NULL: error of the last failed b2t_create */
+int b2t_get_info(const b2t_handle *h, b2t_info *out);
+
+/* PythonHandle.reset() (PythonHandle.cpp:49-71; tetris_environment.py:66-75; vector :55-58).
+ * d_seeds[i] plays the role of time(NULL): only its low 16 bits matter (randomizer.cpp:34-36,47-49). */
+int b2t_reset(b2t_handle *h, const int32_t *d_game_idx, int32_t n, const uint32_t *d_seeds, void *stream);
+
+/* Observation tensors written by step / observe / expand: the reference's state_dict for BOTH players
+ * (state_processors.py:23-54; layout consumed by agents/agent_utils/state_unpack.py:88-105).  Any pointer may be NULL. */
+typedef struct {
+    uint8_t *d_field;      /* [rows, 2, H, W]  field>0 */
+    uint8_t *d_vec;        /* [rows, 2, 19]    x, y, incoming_lines, min(25000,combo_time+50)//100, combo_count, nextpiece 1-hot, piece 1-hot */
+    uint8_t *d_piece_idx;  /* [rows, 2] */
+    int32_t *d_scalars;    /* [rows, 2, 8] raw State views (PythonHandle.h:54-82): x,y,inc_lines,combo_time,combo_count,nextpiece,reward,dead */
+} b2t_obs;
+
+/* tetris_environment.perform_action for n games at once (tetris_environment.py:102-116; vector :79-86):
+ * PythonHandle.make_action (the acting player's keys, null action for the other; PythonHandle.cpp:138-147,73-112)
+ * then, if finalize, PythonHandle.finish_action(time_ms) (PythonHandle.cpp:149-188). */
+typedef struct {
+    const int32_t *d_game_idx;     /* NULL or [n] */
+    int32_t n;
+    const uint8_t *d_player;       /* [n] acting player 0/1 */
+    /* action, one of: */
+    const uint8_t *d_keys;         /* [n, lmax] key codes 0..10 (others ignored, PythonHandle.cpp:109-110) */
+    const uint8_t *d_key_len;      /* [n] */
+    int32_t lmax;
+    const int32_t *d_placement;    /* [n] index into the list of the last b2t_enumerate/b2t_expand of that game */
+    int32_t finalize;              /* simulate/finalize switch of perform_action; 1 = normal step */
+    int32_t time_ms;               /* <=0: cfg.time_ms_per_action */
+    const uint32_t *d_reset_seeds; /* optional [n]: games that end in this call are reset with these seeds right
+                                      after their reward/done are produced (fused worker-loop reset, worker.py:157-160) */
+    /* results */
+    int8_t *d_reward;              /* [n] base term of reward_fcn: 0, or youdead-medead when done (tetris_environment.py:135-144) */
+    uint8_t *d_done;               /* [n] */
+    uint8_t *d_lines;              /* [n,2] states[p].reward = lines cleared since the previous finish (PythonHandle.cpp:176) */
+    b2t_obs obs;                   /* state after the call (after the fused reset, if any) */
+} b2t_step_args;
+int b2t_step(b2t_handle *h, const b2t_step_args *a, void *stream);
+
+/* get_state + state_dict (tetris_environment.py:131-133; vector :99-101) */
+int b2t_observe(b2t_handle *h, const int32_t *d_game_idx, int32_t n, const b2t_obs *obs, void *stream);
+
+/* get_actions: TestField::getMask(2) + action_list de-duplication / null handling
+ * (tetris_environment.py:77-85, TestField.cpp:64-187, data_types/action_list.py:4-20).
+ * The lists stay cached per game (for d_placement / b2t_expand).  d_K [n]; optional d_keys [n,kmax,lmax], d_key_len [n,kmax]. */
+int b2t_enumerate(b2t_handle *h, const int32_t *d_game_idx, int32_t n, const uint8_t *d_player, int32_t *d_K,
+                  uint8_t *d_keys, uint8_t *d_key_len, int32_t kmax, int32_t lmax, void *stream);
+
+/* simulate_all_actions (tetris_environment.py:87-100,127-129): enumerate, then every placement replayed on a scratch
+ * copy of its game (finalize as in perform_action) — the all-placements world model.  Compact output: placement j of
+ * board i sits at row d_offsets[i]+j; rows >= capacity are dropped and reported through *d_total > capacity. */
+typedef struct {
+    const int32_t *d_game_idx;
+    int32_t n;
+    const uint8_t *d_player;   /* [n] */
+    int32_t finalize;
+    int32_t time_ms;
+    int32_t capacity;          /* rows available in the output arrays */
+    int32_t *d_K;              /* [n] */
+    int32_t *d_offsets;        /* [n+1] exclusive prefix sum of K; d_offsets[n] = total */
+    int32_t *d_board;          /* optional [capacity] board i of each row */
+    uint8_t *d_keys;           /* optional [capacity, lmax] */
+    uint8_t *d_key_len;        /* optional [capacity] */
+    int32_t lmax;
+    int8_t *d_reward;          /* optional [capacity] */
+    uint8_t *d_done;           /* optional [capacity] */
+    uint8_t *d_lines;          /* optional [capacity,2] */
+    b2t_obs obs;               /* rows = placements */
+} b2t_expand_args;
+int b2t_expand(b2t_handle *h, const b2t_expand_args *a, void *stream);
+
+/* PythonHandle.copy() / PythonHandle.set() for the whole vector (PythonHandle.cpp:36-42; tetris_environment.py:165-176) */
+int b2t_snapshot(b2t_handle *h, int32_t slot, void *stream);
+int b2t_restore(b2t_handle *h, int32_t slot, void *stream);
+
+/* Pickling equivalent (PythonHandle.h:283-308; drl_tetris/runner.py:69-88): packed state of game g, state_bytes each. */
+int b2t_export_state(b2t_handle *h, int32_t game, void *h_buf, void *stream);
+int b2t_import_state(b2t_handle *h, int32_t game, const void *h_buf, void *stream);
+
+/* The writable numpy views the front-end pokes (data_types/state.py:9-17 dead[0]=1; scripts/eval.py:156 field[:,:]=0) */
+int b2t_poke_dead(b2t_handle *h, int32_t game, int32_t player, int32_t dead, void *stream);
+int b2t_clear_field(b2t_handle *h, int32_t game, int32_t player, void *stream);
+
+/* Episode counters accumulated by b2t_step since creation, for an end-of-rollout reduction across ranks:
+ * [0] env-steps [1] episodes ended [2] wins player0 [3] wins player1 [4] both dead [5] lines cleared
+ * [6] games whose garbage queue overflowed its 6 entries [7] games that outran a stream table.  h_out[8]. */
+int b2t_stats(b2t_handle *h, uint64_t *h_out, void *stream);
+
+/* ---- host-buffer entry points (what a ctypes / pybind11 shim that owns numpy arrays calls) ----
+ * Same semantics as above with HOST pointers; copies go through pinned staging owned by the handle. */
+int b2t_reset_host(b2t_handle *h, const int32_t *h_game_idx, int32_t n, const uint32_t *h_seeds);
+int b2t_step_host(b2t_handle *h, const int32_t *h_game_idx, int32_t n, const uint8_t *h_player, const uint8_t *h_keys,
+                  const uint8_t *h_key_len, int32_t lmax, const int32_t *h_placement, int32_t finalize, int32_t time_ms,
+                  const uint32_t *h_reset_seeds, int8_t *h_reward, uint8_t *h_done, uint8_t *h_lines,
+                  uint8_t *h_field, uint8_t *h_vec, uint8_t *h_piece_idx, int32_t *h_scalars);
+int b2t_observe_host(b2t_handle *h, const int32_t *h_game_idx, int32_t n, uint8_t *h_field, uint8_t *h_vec,
+                     uint8_t *h_piece_idx, int32_t *h_scalars);
+int b2t_enumerate_host(b2t_handle *h, const int32_t *h_game_idx, int32_t n, const uint8_t *h_player, int32_t *h_K,
+                       uint8_t *h_keys, uint8_t *h_key_len, int32_t kmax, int32_t lmax);
+/* rows written = min(total, capacity); *h_total = total */
+int b2t_expand_host(b2t_handle *h, const int32_t *h_game_idx, int32_t n, const uint8_t *h_player, int32_t finalize,
+                    int32_t time_ms, int32_t capacity, int32_t *h_K, int32_t *h_offsets, int32_t *h_total,
+                    uint8_t *h_keys, uint8_t *h_key_len, int32_t lmax, int8_t *h_reward, uint8_t *h_done, uint8_t *h_lines,
+                    uint8_t *h_field, uint8_t *h_vec, uint8_t *h_piece_idx);
+
+/* Stream-table probe for tests: first n entries of the piece / hole stream of a 16-bit seed. */
+int b2t_debug_streams(b2t_handle *h, uint32_t seed16, int32_t n, uint8_t *h_pieces, uint8_t *h_holes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200TETRIS_H */

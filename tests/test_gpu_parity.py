@@ -1,0 +1,322 @@
+"""GPU parity gate: the CUDA engine, called through the C ABI (libb200tetris.so), against the oracle on the same seeded
+inputs, against the committed reference goldens, and — at BASELINE.json's full sizes — through size-independent
+properties.  Bit-exact everywhere (integer/byte work)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import harness
+import pyoracle
+
+pytestmark = pytest.mark.gpu
+
+ALL7 = (0, 1, 2, 3, 4, 5, 6)
+ROLLOUTS = [
+    ("random", 22, 10, ALL7, 256, 160, 0),
+    ("greedy", 22, 10, ALL7, 48, 400, 0),
+    ("greedy", 22, 10, ALL7, 32, 300, 23),
+    ("junk", 22, 10, ALL7, 64, 300, 11),
+    ("sventon", 22, 10, ALL7, 64, 150, 0),
+    ("random", 16, 8, (0, 6), 96, 200, 0),
+    ("greedy", 16, 8, (0, 6), 32, 300, 0),
+    ("random", 40, 20, ALL7, 40, 200, 0),
+    ("greedy", 40, 20, ALL7, 8, 200, 0),
+    ("junk", 40, 20, ALL7, 16, 150, 7),
+    ("random", 10, 6, (2, 3), 64, 150, 0),
+    ("greedy", 10, 6, (2, 3, 4, 5), 32, 200, 0),
+    ("junk", 12, 5, (4,), 33, 150, 5),
+]
+
+
+def _engine(n, H=22, W=10, pieces=ALL7, **kw):
+    from b200vec import B200Vector
+    return B200Vector(n, H, W, pieces, **kw)
+
+
+@pytest.mark.parametrize("kind,H,W,pieces,n,steps,solo", ROLLOUTS)
+def test_rollout_matches_oracle(kind, H, W, pieces, n, steps, solo):
+    kmax, lmax = (256, 64) if W > 10 else (96, 32)
+    lead = pyoracle.OracleVector(n, H, W, pieces)
+    dev = _engine(n, H, W, pieces)
+    stats = harness.rollout_pair(lead, dev, steps, harness.Policy(kind, kmax=kmax, lmax=lmax, solo_period=solo))
+    assert stats["steps"] == n * steps
+    st = dev.e.stats()
+    assert st["garbage_queue_overflow"] == 0 and st["capacity_overflow"] == 0, st
+    if kind == "greedy" and W >= 8:
+        assert stats["lines"] > 0 and stats["garbage"] > 0
+
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_replays_reference_golden(path):
+    g = np.load(path)
+    eng = _engine(int(g["n"]), int(g["H"]), int(g["W"]), tuple(int(x) for x in g["pieces"]))
+    harness.replay_golden(eng, g)
+
+
+def test_config_c2_4096_games_bit_exact():
+    """BASELINE config 2: 4096 parallel 2-player 10x22 games, random placements, diffed against the oracle every step."""
+    n, steps = 4096, 96
+    lead = pyoracle.OracleVector(n)
+    dev = _engine(n)
+    stats = harness.rollout_pair(lead, dev, steps, harness.Policy("random", kmax=96, lmax=32))
+    assert stats["dones"] > 1000
+
+
+@pytest.mark.parametrize("finalize", [True, False])
+@pytest.mark.parametrize("H,W,pieces", [(22, 10, ALL7), (16, 8, (0, 6)), (40, 20, ALL7)])
+def test_world_model_matches_oracle(H, W, pieces, finalize):
+    """simulate_all_actions (b2t_expand) on boards reached by greedy play."""
+    n = 24 if W <= 10 else 6
+    kmax, lmax = (256, 64) if W > 10 else (96, 32)
+    lead = pyoracle.OracleVector(n, H, W, pieces)
+    dev = _engine(n, H, W, pieces)
+    pol = harness.Policy("greedy", kmax=kmax, lmax=lmax)
+    checked = [0]
+
+    def check(t, *_):
+        if t % 9 != 4:
+            return
+        player = pol.players(n, t + 1, np.arange(n))
+        a = lead.expand(player, finalize=finalize, kmax=kmax, lmax=lmax)
+        b = dev.expand(player, finalize=finalize, kmax=kmax, lmax=lmax)
+        assert a["bad"] == 0
+        assert b["total"] == int(a["K"].sum())
+        for k in ("K", "keys", "key_len", "reward", "done", "lines", "field", "vec", "piece_idx"):
+            harness.assert_same("expand." + k, t, a[k], b[k])
+        checked[0] += int(a["K"].sum())
+
+    harness.rollout_pair(lead, dev, 100, pol, on_step=check)
+    assert checked[0] > 500
+
+
+def test_bar_null_moves_false():
+    n = 64
+    lead = pyoracle.OracleVector(n)
+    dev = _engine(n, bar_null_moves=False)
+    s = harness.seeds_for(np.arange(n), np.zeros(n, int))
+    lead.reset(s); dev.reset(s)
+    pl = (np.arange(n) & 1).astype(np.uint8)
+    a = lead.enumerate(pl, bar_null_moves=False, kmax=96, lmax=32)
+    b = dev.enumerate(pl, bar_null_moves=False, kmax=96, lmax=32)
+    for x, y in zip(a[:3], b[:3]):
+        assert np.array_equal(x, y)
+
+
+def test_stream_tables_match_oracle():
+    from b200tetris import Engine
+    for pieces in (ALL7, (0, 6), (2, 3), (2, 3, 4, 5)):
+        e = Engine(1, pieces=pieces, piece_stream_len=700, hole_stream_len=64)
+        for seed in (0, 1, 1000, 32767, 32768, 40000, 65535):
+            p, h = e.debug_streams(seed, 700)
+            assert np.array_equal(p, pyoracle.piece_stream(seed, pieces, 700)), (pieces, seed)
+            assert np.array_equal(h[:64], pyoracle.hole_stream(seed, 10, 64)), (pieces, seed)
+        e.close()
+
+
+def test_unaligned_key_width_and_subsets():
+    """keys arrays whose width is not a multiple of 16 take the byte path; game subsets in arbitrary order."""
+    n = 80
+    lead = pyoracle.OracleVector(n)
+    dev = _engine(n)
+    s = harness.seeds_for(np.arange(n), np.zeros(n, int))
+    lead.reset(s); dev.reset(s)
+    rng = np.random.RandomState(3)
+    for t in range(40):
+        ids = rng.permutation(n)[: rng.randint(1, n)].astype(np.int32)
+        pl = rng.randint(0, 2, len(ids)).astype(np.uint8)
+        keys = rng.randint(0, 12, (len(ids), 21)).astype(np.uint8)
+        ln = rng.randint(0, 22, len(ids)).astype(np.uint8)
+        ra = lead.step(pl, keys, ln, ids)
+        rb = dev.step(pl, keys, ln, ids)
+        for x, y in zip(ra, rb):
+            assert np.array_equal(x, y)
+        for x, y in zip(lead.observe(), dev.observe()):
+            if t > 0:
+                assert np.array_equal(x, y)
+        d = ids[ra[1].astype(bool)]
+        if len(d):
+            s2 = rng.randint(0, 1 << 16, len(d)).astype(np.uint32)
+            lead.reset(s2, d); dev.reset(s2, d)
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+def _digest_dev(t):
+    return harness.digest(t.cpu().numpy())
+
+
+def test_full_size_properties_1m_games():
+    """BASELINE config 4 (2^20 games): (a) results do not depend on how the batch is split into calls, (b) a step from a
+    snapshot is reproducible, (c) stepping by placement index == stepping by the enumerated keys, (d) the fused reset of
+    finished games == step followed by reset, (e) the sampled games agree with the oracle."""
+    import torch
+    from b200tetris import Engine
+    n = 1 << 20
+    dev = torch.device("cuda:0")
+    e = Engine(n)
+    gid = torch.arange(n, device=dev, dtype=torch.int64)
+    seeds = torch.from_numpy(harness.seeds_for(np.arange(n), np.zeros(n, int)).astype(np.int64)).to(dev).to(torch.int32)
+    e.reset_dev(seeds.view(torch.int32))
+    K = torch.empty(n, dtype=torch.int32, device=dev)
+    reward = torch.empty(n, dtype=torch.int8, device=dev); done = torch.empty(n, dtype=torch.uint8, device=dev)
+    lines = torch.empty((n, 2), dtype=torch.uint8, device=dev)
+    field = torch.empty((n, 2, 22, 10), dtype=torch.uint8, device=dev); vec = torch.empty((n, 2, 19), dtype=torch.uint8, device=dev)
+    sample = np.arange(0, n, 4099)[:250].astype(np.int32)
+    lead = pyoracle.OracleVector(len(sample))
+    lead.reset(harness.seeds_for(sample, np.zeros(len(sample), int)))
+    keys_all = torch.empty((n, 96, 32), dtype=torch.uint8, device=dev) if False else None
+    for t in range(24):
+        player = ((gid + t) & 1).to(torch.uint8)
+        e.enumerate_dev(player, K)
+        h = torch.from_numpy(harness.splitmix64(1, np.arange(n), t).astype(np.int64)).to(dev)
+        sel = (h.remainder(1 << 30) % K.to(torch.int64)).to(torch.int32)
+        if t == 10:
+            e.snapshot(0)
+        e.step_dev(player, placement=sel, reward=reward, done=done, lines=lines, field=field, vec=vec)
+        torch.cuda.synchronize()
+        if t == 10:
+            ref = (_digest_dev(reward), _digest_dev(done), _digest_dev(field), _digest_dev(vec))
+            # (b) reproducible from the snapshot, (a) in two half-batches given as explicit index lists
+            e.restore(0)
+            e.enumerate_dev(player, K)
+            half = n // 2
+            for lo, hi in ((0, half), (half, n)):
+                idx = torch.arange(lo, hi, device=dev, dtype=torch.int32)
+                e.step_dev(player[lo:hi].contiguous(), idx=idx, placement=sel[lo:hi].contiguous(), reward=reward[lo:hi], done=done[lo:hi],
+                           lines=lines[lo:hi], field=field[lo:hi], vec=vec[lo:hi])
+            torch.cuda.synchronize()
+            assert ref == (_digest_dev(reward), _digest_dev(done), _digest_dev(field), _digest_dev(vec))
+        # (e) oracle on the sample, driven by the same placement indices
+        Ko, keys_o, klen_o = lead.enumerate(player[sample].cpu().numpy())[:3]
+        assert np.array_equal(Ko, K[sample].cpu().numpy())
+        so = sel[sample].cpu().numpy()
+        ro = lead.step(player[sample].cpu().numpy(), keys_o[np.arange(len(sample)), so], klen_o[np.arange(len(sample)), so])
+        assert np.array_equal(ro[0], reward[sample].cpu().numpy()) and np.array_equal(ro[1], done[sample].cpu().numpy())
+        fo = lead.observe()
+        assert np.array_equal(fo[0], field[sample].cpu().numpy())
+        if t > 0:
+            assert np.array_equal(fo[1], vec[sample].cpu().numpy())
+        d = done.bool()
+        if d.any():
+            ids = torch.nonzero(d).flatten().to(torch.int32)
+            s2 = torch.from_numpy(harness.seeds_for(ids.cpu().numpy(), np.full(ids.numel(), t + 1)).astype(np.int64)).to(dev).to(torch.int32)
+            e.reset_dev(s2, ids)
+            ds = np.nonzero(ro[1])[0]
+            if len(ds):
+                lead.reset(harness.seeds_for(sample[ds], np.full(len(ds), t + 1)), ds)
+    torch.cuda.synchronize()
+    st = e.stats()
+    assert st["garbage_queue_overflow"] == 0 and st["capacity_overflow"] == 0 and st["env_steps"] >= 24 * n - st["episodes"] * 2
+    e.close()
+
+
+def test_fused_reset_equals_step_then_reset():
+    n = 2048
+    a = _engine(n); b = _engine(n)
+    s = harness.seeds_for(np.arange(n), np.zeros(n, int))
+    a.reset(s); b.reset(s)
+    pol = harness.Policy("random", kmax=96, lmax=32)
+    gids = np.arange(n)
+    for t in range(70):
+        pl = pol.players(n, t, gids)
+        keys, ln, _ = pol.choose(a, t, gids, pl)
+        s2 = harness.seeds_for(gids, np.full(n, t + 1))
+        ra = a.e.step(pl, keys, ln, reset_seeds=s2, want_obs=True)
+        rb = b.e.step(pl, keys, ln)
+        d = np.nonzero(rb[1])[0]
+        if len(d):
+            b.reset(s2[d], d)
+        ob = b.observe()
+        assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
+        assert np.array_equal(ra[3][0], ob[0]) and np.array_equal(ra[3][2], ob[2])
+        if t > 0:
+            assert np.array_equal(ra[3][1], ob[1])
+
+
+def test_snapshot_export_import_roundtrip():
+    n = 300
+    a = _engine(n)
+    s = harness.seeds_for(np.arange(n), np.zeros(n, int))
+    a.reset(s)
+    pol = harness.Policy("random", kmax=96, lmax=32)
+    gids = np.arange(n)
+    for t in range(10):
+        pl = pol.players(n, t, gids)
+        keys, ln, _ = pol.choose(a, t, gids, pl)
+        a.step(pl, keys, ln)
+    before = a.observe()
+    a.e.snapshot(1)
+    blob = a.e.export_state(17)
+    assert blob.size == a.e.state_bytes
+    pl = pol.players(n, 10, gids)
+    keys, ln, _ = pol.choose(a, 10, gids, pl)
+    r1 = a.step(pl, keys, ln); after = a.observe()
+    a.e.restore(1)
+    for x, y in zip(before, a.observe()):
+        assert np.array_equal(x, y)
+    r2 = a.step(pl, keys, ln)
+    for x, y in zip(r1, r2):
+        assert np.array_equal(x, y)
+    for x, y in zip(after, a.observe()):
+        assert np.array_equal(x, y)
+    a.e.import_state(18, blob)       # PythonHandle.set(other): game 18 becomes a copy of (old) game 17
+    a.e.restore(1)
+    a.e.import_state(18, blob)
+    o = a.observe()
+    assert np.array_equal(o[0][18], before[0][17]) and np.array_equal(o[1][18], before[1][17])
+    # state.lock(): dead players' keys are ignored (data_types/state.py:9-17, PythonHandle.cpp:141)
+    a.e.poke_dead(5, 0, True); a.e.poke_dead(5, 1, True)
+    f0 = a.observe(np.array([5]))[0]
+    a.step(np.array([0], np.uint8), np.array([[7] + [0] * 15], np.uint8), np.array([1], np.uint8), np.array([5]), finalize=False)
+    assert np.array_equal(f0, a.observe(np.array([5]))[0])
+
+
+def test_vector_env_front_end():
+    """The reference-shaped surface (tetris_environment_vector names) against the oracle for a short random rollout."""
+    from b200tetris import tetris_environment_vector, action
+    n = 32
+    env = tetris_environment_vector(n, settings={"seed": 1234, "render": False})
+    lead = pyoracle.OracleVector(n)
+    lead.reset(env._seeds(np.arange(n)) if False else _front_seeds(env, n))
+    rng = np.random.RandomState(0)
+    cur = rng.choice([0, 1], n)
+    for t in range(60):
+        cur = 1 - cur
+        acts = env.get_actions(player=list(cur))
+        Ko, keys_o, klen_o = lead.enumerate(cur.astype(np.uint8), kmax=96, lmax=32)[:3]
+        assert [len(a) for a in acts] == list(Ko)
+        sel = [rng.randint(0, len(a)) for a in acts]
+        chosen = [a[s] for a, s in zip(acts, sel)]
+        for i in range(n):
+            assert list(chosen[i]) == list(keys_o[i, sel[i], :klen_o[i, sel[i]]])
+        rewards, dones = env.perform_action(chosen, player=list(cur))
+        ro = lead.step(cur.astype(np.uint8), keys_o[np.arange(n), sel], klen_o[np.arange(n), sel])
+        assert [int(r()) for r in rewards] == list(ro[0]) and dones == [bool(d) for d in ro[1]]
+        st = env.get_state()
+        fo = lead.observe()
+        for i in range(n):
+            for p in (0, 1):
+                d = st[i][p]
+                assert np.array_equal(d["field"], fo[0][i, p]) and d["piece_idx"] == fo[2][i, p]
+                assert np.array_equal(d["nextpiece"], fo[1][i, p, 5:12])
+        ids = [i for i, d in enumerate(dones) if d]
+        if ids:
+            before = env._episode[ids].copy()
+            env.reset(env=ids)
+            lead.reset(_front_seeds(env, n)[ids], np.array(ids, np.int32))
+            assert (env._episode[ids] == before + 1).all()
+    sims = env.simulate_all_actions(env=[0, 1], player=[int(1 - cur[0]), int(1 - cur[1])])
+    assert len(sims) == 2 and len(sims[0]) == len(env.get_actions(env=[0], player=int(1 - cur[0]))[0])
+
+
+def _front_seeds(env, n):
+    """seeds the front-end used for the CURRENT episode of every env (episode counter was already advanced)"""
+    ids = np.arange(n)
+    env._episode[ids] -= 1
+    s = env._seeds(ids)
+    env._episode[ids] += 1
+    return s
