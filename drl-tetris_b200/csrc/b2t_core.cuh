@@ -17,6 +17,10 @@
 //   randomizer.cpp, TestField.cpp:3-415 — cited again at each function.
 #pragma once
 #include <stdint.h>
+#if defined(B2T_BOUNDS_CHECK)
+#include <cstdio>
+#include <cstdlib>
+#endif
 
 #if defined(__CUDACC__)
 #define B2T_HD __host__ __device__ __forceinline__
@@ -139,7 +143,9 @@ template <int H_, int W_> struct Geo {
     static constexpr int SPAWN_X = (W_ - 4) / 2;
     static constexpr int FIELD_BYTES = H_ * W_;
     static constexpr int OBS_FIELD = 2 * H_ * W_;   // bytes of field observation per game
-    static constexpr int KEYW = (W_ > 10 || H_ > 25) ? 8 : 4; // packed key words per placement (4 bit tokens)
+    // A key sequence is at most: rotation + (W-4)/2+1 lateral + [turn] + one lateral per column crossed (<= W-1) with the rows
+    // risen in between (their sum <= H) + the final 7  <=  H + 2W + 4 tokens.  4-bit tokens, whole uint4s.
+    static constexpr int KEYW = (((H_ + 2 * W_ + 4 + 7) / 8 + 3) / 4) * 4;
     static constexpr int LMAX = KEYW * 8;
     static constexpr int KMAX = (W_ > 10) ? 256 : 96;
     B2T_HD static col_t one() { return (col_t)1; }
@@ -224,8 +230,16 @@ template <class G, int S> B2T_HD void board_clear(const Board<G, S>& b) {
 }
 
 // gameField.cpp:10-20 possible(): pcn = column nibbles of the piece at its rotation
+#if defined(B2T_BOUNDS_CHECK) && !defined(__CUDA_ARCH__)
+#define B2T_CHECK_XY(x, y) do { if ((x) < -G::XL || (x) + 3 > G::W + G::XR - 1 || (y) + G::YB < 0 || (y) + G::YB + 4 > G::CBITS) { \
+    fprintf(stderr, "b2t bounds: x=%d y=%d (W=%d H=%d) at %s:%d\n", (int)(x), (int)(y), G::W, G::H, __FILE__, __LINE__); abort(); } } while (0)
+#else
+#define B2T_CHECK_XY(x, y) do { } while (0)
+#endif
+
 template <class G, int S> B2T_HD bool fits(const Board<G, S>& b, int x, int y, uint32_t pcn) {
     typedef typename G::col_t col_t;
+    B2T_CHECK_XY(x, y);
     const col_t* p = b.cols + (x + G::XL) * S;
     const int sh = y + G::YB;
     col_t acc = (p[0] >> sh) & (col_t)(pcn & 15u);
@@ -237,6 +251,7 @@ template <class G, int S> B2T_HD bool fits(const Board<G, S>& b, int x, int y, u
 // bit (y+YB) set  <=>  the piece collides at height y (all heights at once); pcc = cell list
 template <class G, int S> B2T_HD typename G::col_t collide_mask(const Board<G, S>& b, int x, uint32_t pcc) {
     typedef typename G::col_t col_t;
+    B2T_CHECK_XY(x, 0);
     const col_t* p = b.cols + (x + G::XL) * S;
     col_t m = p[(pcc & 3u) * S] >> ((pcc >> 2) & 3u);
     m |= p[((pcc >> 4) & 3u) * S] >> ((pcc >> 6) & 3u);

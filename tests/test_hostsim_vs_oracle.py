@@ -16,6 +16,7 @@ import pyhostsim  # noqa: E402
 
 CASES = [
     ("random", 22, 10, (0, 1, 2, 3, 4, 5, 6), 32, 400, 0),
+    ("random", 22, 10, (0, 1, 2, 3, 4, 5, 6), 256, 60, 0),   # step 20 / game 90 holds a 33-key placement (> the 32 the survey saw)
     ("greedy", 22, 10, (0, 1, 2, 3, 4, 5, 6), 12, 700, 0),
     ("greedy", 22, 10, (0, 1, 2, 3, 4, 5, 6), 8, 500, 23),
     ("junk", 22, 10, (0, 1, 2, 3, 4, 5, 6), 16, 400, 11),
