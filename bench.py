@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — the driver's measurement contract for the b200tetris hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+    python bench.py --impl reference --gpus N ...            # the reference's own CPU backend on the box's host cores
+
+Metric (BASELINE.json): env-steps/s (and placements/s) for 2-player 10x22 Tetris.
+A "step" = one perform_action over every game of the batch: ONE launch of the fused step kernel (acting player's keys,
+finish_action for both players, fused reset of finished games, state write-back, uint8 observation tensors out).
+Workload at N=1: BASELINE configs[3] sharded weakly — 2^20 concurrent games per GPU (state 352 MB + 503 MB of observation per
+step, both far larger than the 126 MB L2, so no flush is needed between iterations); actions are SVENton key strings
+[8]*r+[2]+[3]*t+[7] (agents/sventon_agent/sventon_utils.py:9-13) drawn from a counter hash, resident in HBM before the
+timed region.  The all-placements world model (configs[2], 65 536 boards) is timed in the same run and reported under
+"placements".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "drl-tetris_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+
+H, W = 22, 10
+OBS_BYTES = 2 * (H * W + 19 + 1)                 # 480   
+S_BYTES = 2 * (H * ((W + 7) // 8) + 128)         # 344
+STEP_BYTES = 2 * S_BYTES + OBS_BYTES + 37        # 1205 algorithmic bytes per env-step
+def board_bytes(mean_k):                         # 352 + 520*K per expanded board
+    return S_BYTES + 8 + mean_k * (OBS_BYTES + 32 + 8)
+
+
+def splitmix64(*words):
+    z = np.uint64(0x9E3779B97F4A7C15)
+    with np.errstate(over="ignore"):
+        acc = np.zeros(np.broadcast(*[np.asarray(w) for w in words]).shape, np.uint64)
+        for w in words:
+            acc = acc + np.asarray(w).astype(np.uint64) + z
+            acc = (acc ^ (acc >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            acc = (acc ^ (acc >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            acc = acc ^ (acc >> np.uint64(31))
+    return acc
+
+
+def sventon_keys(gids, t, lmax=32):
+    """[8]*r + [2] + [3]*tr + [7], r in [0,4), tr in [0,W) from a counter hash of (global game id, step)."""
+    h = splitmix64(7, gids, t)
+    r = (h % np.uint64(4)).astype(np.int64)
+    tr = ((h >> np.uint64(8)) % np.uint64(W)).astype(np.int64)
+    n = len(gids)
+    col = np.arange(lmax)[None, :]
+    keys = np.zeros((n, lmax), np.uint8)
+    keys[col < r[:, None]] = 8
+    keys[col == r[:, None]] = 2
+    keys[(col > r[:, None]) & (col <= (r + tr)[:, None])] = 3
+    keys[col == (r + tr + 1)[:, None]] = 7
+    return keys, (r + tr + 2).astype(np.uint8)
+
+
+class ClockSampler(threading.Thread):
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def measured_peak():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(key):
+    """per-launch dram bytes of the dominant kernel from the committed ncu summary, if any"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(key)
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------- CPU legs
+def cpu_port_leg(n=2048, steps=48):
+    """The plain-C oracle (oracle/tetris_oracle.c) on ONE host core, same workload S on a bounded sample."""
+    import pyoracle
+    v = pyoracle.OracleVector(n, H, W)
+    gids = np.arange(n)
+    v.reset((splitmix64(0xB200, gids, 0) & np.uint64(0xFFFF)).astype(np.uint32))
+    pre = [sventon_keys(gids, t) for t in range(steps)]
+    t0 = time.perf_counter()
+    for t in range(steps):
+        keys, ln = pre[t]
+        _, done, _ = v.step(((gids + t) & 1).astype(np.uint8), keys, ln)
+        v.observe()
+        d = np.nonzero(done)[0]
+        if len(d):
+            v.reset((splitmix64(0xB200, d, t + 1) & np.uint64(0xFFFF)).astype(np.uint32), d)
+    dt = time.perf_counter() - t0
+    return n * steps / dt, "%d games x %d steps of workload S incl. state_dict, 1 thread" % (n, steps)
+
+
+def _ref_worker(args):
+    """One process of the compiled reference backend (oracle/_ref/B): raw PythonHandle loop of workload S."""
+    wid, n, steps = args
+    import refmod
+    mod, set_time = refmod.load("B")
+    mod.set_pieces([0, 1, 2, 3, 4, 5, 6])
+    gids = np.arange(n) + wid * n
+    hs = []
+    for g in gids:
+        set_time(int(splitmix64(0xB200, g, 0)) & 0xFFFF)
+        h = mod.PythonHandle(2, [H, W])
+        h.reset()
+        hs.append(h)
+    pre = [sventon_keys(gids, t) for t in range(steps)]
+    pre = [[[int(k) for k in keys[i, :ln[i]]] for i in range(n)] for keys, ln in pre]
+    t0 = time.perf_counter()
+    for t in range(steps):
+        acts = pre[t]
+        for i, h in enumerate(hs):
+            p = (int(gids[i]) + t) & 1
+            a = [[0], [0]]
+            a[p] = acts[i]
+            h.make_action(a)
+            if h.finish_action(400):
+                set_time(int(splitmix64(0xB200, gids[i], t + 1)) & 0xFFFF)
+                h.reset()
+    return n * steps, time.perf_counter() - t0
+
+
+def reference_leg(steps, per_proc_games=64, per_proc_steps=40):
+    """The reference's own C++ backend (unmodified, compiled -O2 into oracle/_ref/B) on every host core."""
+    import multiprocessing as mp
+    import refmod
+    cores = os.cpu_count() or 1
+    if not refmod.available("B"):
+        v, sample = cpu_port_leg()
+        return v, 1, "port", sample
+    ctx = mp.get_context("spawn")
+    vals = []
+    with ctx.Pool(cores) as pool:
+        for _ in range(max(1, steps)):
+            res = pool.map(_ref_worker, [(w, per_proc_games, per_proc_steps) for w in range(cores)])
+            vals.append(sum(r[0] for r in res) / max(r[1] for r in res))
+    return float(np.median(vals)), cores, "reference", "%d procs x %d games x %d steps of workload S, raw PythonHandle make_action+finish_action loop (no Python front-end, no state copies)" % (cores, per_proc_games, per_proc_steps)
+
+
+# ---------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--games", type=int, default=1 << 20, help="games per GPU")
+    ap.add_argument("--boards", type=int, default=1 << 16, help="boards per GPU for the world-model leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip placements / e2e / cpu legs (profiling runs)")
+    ap.add_argument("--leg", default="all", help="all | step | placements  (profiling runs: time only one leg)")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    a.warmup = max(a.warmup, 3)
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        v, cores, kind, sample = reference_leg(a.steps)
+        print(json.dumps({"impl": "reference", "metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s", "n_gpus": a.gpus,
+                          "steps": a.steps, "warmup": a.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "config": {"workload": "S: SVENton key strings, 2-player 22x10, reset on done; reference CPU backend on host cores"},
+                          "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample},
+                          "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from b200tetris import Engine
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = a.games
+    gids = np.arange(n, dtype=np.int64) + rank * n           # GLOBAL game ids: results do not depend on the sharding
+    eng = Engine(n, H, W, device=local)
+    R = 4                                                     # ring of pre-generated action / seed tensors
+    keys_r, len_r, seed_r = [], [], []
+    for t in range(R):
+        k, ln = sventon_keys(gids, t)
+        keys_r.append(torch.from_numpy(k).to(dev)); len_r.append(torch.from_numpy(ln).to(dev))
+        seed_r.append(torch.from_numpy((splitmix64(0xB200, gids, t + 1) & np.uint64(0xFFFF)).astype(np.int64)).to(dev).to(torch.int32))
+    player_r = [torch.from_numpy(((gids + t) & 1).astype(np.uint8)).to(dev) for t in range(2)]
+    reward = torch.empty(n, dtype=torch.int8, device=dev); done = torch.empty(n, dtype=torch.uint8, device=dev)
+    lines = torch.empty((n, 2), dtype=torch.uint8, device=dev)
+    field = torch.empty((n, 2, H, W), dtype=torch.uint8, device=dev); vec = torch.empty((n, 2, 19), dtype=torch.uint8, device=dev)
+    pidx = torch.empty((n, 2), dtype=torch.uint8, device=dev)
+    eng.reset_dev(torch.from_numpy((splitmix64(0xB200, gids, 0) & np.uint64(0xFFFF)).astype(np.int64)).to(dev).to(torch.int32))
+
+    def one_step(t):
+        eng.step_dev(player_r[t & 1], keys_r[t % R], len_r[t % R], reset_seeds=seed_r[t % R], reward=reward, done=done, lines=lines,
+                     field=field, vec=vec, piece_idx=pidx)
+
+    for t in range(a.warmup):
+        one_step(t)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+    torch.cuda.synchronize()
+    ev[0].record()
+    for t in range(a.steps):
+        one_step(a.warmup + t)
+        ev[t + 1].record()
+    torch.cuda.synchronize()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.steps)]
+    clocks = sampler.summary()
+    tmax = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tmax.item())
+    value = n * world * a.steps / (total_ms_max * 1e-3)
+    peak, peak_src = measured_peak()
+    k_ms = float(np.mean(per_launch_ms))
+    achieved = STEP_BYTES * n / (k_ms * 1e-3) / 1e9
+    stats = eng.stats()
+
+    out = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+           "ms_per_step": total_ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+           "data": "synthetic",
+           "config": {"workload": "C4 (BASELINE configs[3], weak): %d concurrent 2-player 22x10 games per GPU, all 7 pieces, workload S "
+                                  "(SVENton key strings from a counter hash), fused reset of finished games, uint8 observation tensors "
+                                  "for both players written every step" % n,
+                      "games_per_gpu": n, "l2": "working set per step (352 MB state + 503 MB observations) exceeds the 126 MB L2; no flush",
+                      "episodes_ended": stats["episodes"], "lines_cleared": stats["lines"]},
+           "clocks": clocks, "gpu_launches": a.steps,
+           "roofline": {"bound": "hbm", "kernel": "game_kernel<22,10> (fused step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "peak_source": peak_src, "algorithmic_bytes_per_env_step": STEP_BYTES,
+                        "launch_ms": k_ms, "traffic": ncu_traffic("step_bytes_per_launch")}}
+
+    if a.leg == "step":
+        a.no_extras = True
+    if not a.no_extras and a.leg == "all":
+        # ---- end-to-end through the C ABI with HOST buffers (b2t_step_host): H2D of the step's inputs, D2H of reward/done and
+        # of the observation tensors, inside the timed region
+        e2e_steps = max(2, min(a.steps, 5))
+        hk = [(keys_r[t % R].cpu().numpy(), len_r[t % R].cpu().numpy(), seed_r[t % R].cpu().numpy().astype(np.uint32),
+               player_r[t & 1].cpu().numpy()) for t in range(R)]
+        def host_step(t, want_obs):
+            k, ln, sd, pl = hk[t % R]
+            return eng.step(pl, k, ln, reset_seeds=sd, want_obs=want_obs)
+        host_step(0, True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for t in range(e2e_steps):
+            host_step(t + 1, True)
+        dt_full = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for t in range(e2e_steps):
+            host_step(t + 1, False)
+        dt_lite = time.perf_counter() - t0
+        e2e = torch.tensor([dt_full, dt_lite], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+        h2d = n * (32 + 1 + 1 + 4)
+        out["e2e"] = {"value": n * world * e2e_steps / float(e2e[0]), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": n * (4 + OBS_BYTES), "steps": e2e_steps,
+                      "api": "b2t_step_host (numpy in/out through the handle's pinned staging), observations copied back every step",
+                      "without_observation_copy": {"value": n * world * e2e_steps / float(e2e[1]), "d2h_bytes_per_step": n * 4}}
+
+    if not a.no_extras:
+        # ---- world model: BASELINE configs[2], 65 536 boards reached by 8..40 plies of random placements
+        nb = a.boards
+        w = Engine(nb, H, W, device=local)
+        bg = np.arange(nb, dtype=np.int64) + rank * nb
+        w.reset_dev(torch.from_numpy((splitmix64(0xC3, bg, 0) & np.uint64(0xFFFF)).astype(np.int64)).to(dev).to(torch.int32))
+        K = torch.empty(nb, dtype=torch.int32, device=dev); offs = torch.empty(nb + 1, dtype=torch.int32, device=dev)
+        plies = torch.from_numpy((8 + splitmix64(0xC3, bg, 1) % np.uint64(32)).astype(np.int64)).to(dev)
+        gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
+        bd = torch.empty(nb, dtype=torch.uint8, device=dev)
+        for t in range(40):
+            pl = torch.from_numpy(((bg + t) & 1).astype(np.uint8)).to(dev)
+            w.enumerate_dev(pl, K)
+            sel = (torch.randint(0, 1 << 30, (nb,), device=dev, generator=gen) % K.to(torch.int64)).to(torch.int32)
+            act = torch.nonzero(plies > t).flatten().to(torch.int32)
+            if act.numel() == 0:
+                break
+            w.step_dev(pl[act.long()].contiguous(), idx=act, placement=sel[act.long()].contiguous(), done=bd[: act.numel()])
+            # finished games simply restart
+            dn = act[bd[: act.numel()].bool()]
+            if dn.numel():
+                w.reset_dev(torch.randint(0, 1 << 16, (dn.numel(),), device=dev, generator=gen).to(torch.int32), dn)
+        side = torch.from_numpy(((bg + 40) & 1).astype(np.uint8)).to(dev)
+        cap = nb * 40
+        pf = torch.empty((cap, 2, H, W), dtype=torch.uint8, device=dev); pv = torch.empty((cap, 2, 19), dtype=torch.uint8, device=dev)
+        pp = torch.empty((cap, 2), dtype=torch.uint8, device=dev); pk = torch.empty((cap, 32), dtype=torch.uint8, device=dev)
+        pl_ = torch.empty(cap, dtype=torch.uint8, device=dev); pr = torch.empty(cap, dtype=torch.int8, device=dev)
+        pd = torch.empty(cap, dtype=torch.uint8, device=dev); pb = torch.empty(cap, dtype=torch.int32, device=dev)
+
+        def expand(fin=True):
+            w.expand_dev(side, K, offs, cap, finalize=fin, board=pb, keys=pk, key_len=pl_, reward=pr, done=pd, field=pf, vec=pv, piece_idx=pp)
+
+        for _ in range(3):
+            expand()
+        torch.cuda.synchronize()
+        total = int(offs[-1].item())
+        assert total <= cap, "placement capacity exceeded"
+        reps = max(3, min(a.steps, 10))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            expand()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        pt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+        ms = float(pt.item())
+        mean_k = total / nb
+        ach = board_bytes(mean_k) * nb / (ms * 1e-3) / 1e9
+        out["placements"] = {"metric": "placements_per_sec", "value": total * world / (ms * 1e-3), "unit": "placements/s",
+                             "boards_per_sec": nb * world / (ms * 1e-3), "boards_per_gpu": nb, "mean_K": mean_k, "ms_per_expand": ms,
+                             "finalize": True, "gpu_launches_per_expand": 5,
+                             "workload": "C3 (BASELINE configs[2]): %d boards after 8..40 plies of random placements; enumerate + scan + "
+                                         "expand(finalize=1) with uint8 tensors, keys, reward, done for every placement" % nb,
+                             "roofline": {"bound": "hbm", "kernel": "enumerate_kernel + game_kernel<22,10> (expand)", "achieved": ach, "peak": peak,
+                                          "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_board": board_bytes(mean_k),
+                                          "traffic": ncu_traffic("expand_bytes_per_launch")}}
+        w.close()
+        if rank == 0 and a.leg == "all":
+            v, sample = cpu_port_leg()
+            out["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port", "sample": sample}
+    if rank == 0:
+        print(json.dumps(out))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

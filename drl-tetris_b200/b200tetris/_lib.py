@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200tetris.so")
+LIB_PATH = os.environ.get("B2T_LIB") or os.path.join(_HERE, "libb200tetris.so")   # B2T_LIB: experimental builds (build.py --out)
 
 VEC_LEN = 19
 SNAPSHOT_SLOTS = 4

@@ -41,15 +41,21 @@ def _compile(args):
     return obj
 
 
-def build(force=False, verbose=True):
+def build(force=False, verbose=True, out=None, defines=(), only=None):
+    """out/defines/only: build an experimental variant (python build.py --out libx.so -DB2T_GAME_MINB=5 --only 22x10)"""
+    global OUT, OBJ
+    if out:
+        OUT = os.path.join(HERE, "b200tetris", out)
+        OBJ = os.path.join(HERE, "build", os.path.splitext(out)[0])
+        force = True
     os.makedirs(OBJ, exist_ok=True)
     newest = max(_newest_source(), os.path.getmtime(os.path.join(HERE, "..", "include", "b200tetris.h")), os.path.getmtime(__file__))
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) > newest:
         return OUT
-    jobs = [(os.path.join(CSRC, "b2t_api.cu"), os.path.join(OBJ, "b2t_api.o"), [])]
+    jobs = [(os.path.join(CSRC, "b2t_api.cu"), os.path.join(OBJ, "b2t_api.o"), list(defines))]
     for h, w in geometries():
         jobs.append((os.path.join(CSRC, "b2t_geom_inst.cu"), os.path.join(OBJ, "b2t_geom_%d_%d.o" % (h, w)),
-                     ["-DB2T_H=%d" % h, "-DB2T_W=%d" % w]))
+                     ["-DB2T_H=%d" % h, "-DB2T_W=%d" % w] + list(defines)))
     with cf.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
         objs = list(ex.map(_compile, jobs))
     cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs + ["-cudart", "static"]
@@ -62,4 +68,6 @@ def build(force=False, verbose=True):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv)
+    argv = sys.argv[1:]
+    out = argv[argv.index("--out") + 1] if "--out" in argv else None
+    build(force="--force" in argv, out=out, defines=[x for x in argv if x.startswith("-D")])

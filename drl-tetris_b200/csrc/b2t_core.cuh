@@ -447,9 +447,13 @@ B2T_HD int gq_total(const PS& s) {  // :9-14
 }
 B2T_HD void gq_add(PS& s, int amount, int32_t t) {  // :22-24
     if (s.gq_n >= GQ_CAP) { s.flags |= 1; return; }  // sticky overflow, surfaced through b2t_status
+    // select form on every slot: a conditional store would be turned into a dynamically indexed one, which drags the
+    // whole register-resident game state into local memory
 #pragma unroll
-    for (int i = 0; i < GQ_CAP; i++)
-        if (i == s.gq_n) { s.gq_count[i] = (int16_t)amount; s.gq_delay[i] = t + 1000; }
+    for (int i = 0; i < GQ_CAP; i++) {
+        s.gq_count[i] = (i == s.gq_n) ? (int)(int16_t)amount : s.gq_count[i];
+        s.gq_delay[i] = (i == s.gq_n) ? t + 1000 : s.gq_delay[i];
+    }
     s.gq_n++;
 }
 B2T_HD int gq_block(PS& s, int amount, int32_t t, bool freeze) {  // :26-52
@@ -719,6 +723,7 @@ B2T_HD void observe_vec(const PS& s, uint8_t* v) {
     const uint32_t ct = (uint32_t)(s.remaining + 50) & 0xFFFFu;
     v[3] = (uint8_t)((ct < 25000u ? ct : 25000u) / 100u);
     v[4] = (uint8_t)s.combo_count;
+#pragma unroll
     for (int k = 0; k < 7; k++) { v[5 + k] = (s.next == k); v[12 + k] = (s.kind == k); }
 }
 

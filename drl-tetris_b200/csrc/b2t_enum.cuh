@@ -23,9 +23,9 @@ template <int KW> struct Seq {
         n = 0;
     }
     B2T_HD void push(uint32_t tok) {  // append at nibble n
+        const uint32_t v = tok << (4 * (n & 7));
 #pragma unroll
-        for (int i = 0; i < KW; i++)
-            if ((n >> 3) == i) w[i] |= tok << (4 * (n & 7));
+        for (int i = 0; i < KW; i++) w[i] |= ((n >> 3) == i) ? v : 0u;   // select form: keeps w[] in registers
         n++;
     }
     B2T_HD void push_front(uint32_t tok) {  // prepend: everything moves up one nibble

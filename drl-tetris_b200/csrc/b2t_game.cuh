@@ -114,10 +114,18 @@ template <class G, int S> B2T_HD void game_reset(Game<G, S>& g, const Tabs& tb, 
 
 // Convert u8 keys (any value; >10 are no-ops like PythonHandle.cpp:109-110) to packed tokens
 template <int KW> B2T_HD void pack_keys(const uint8_t* keys, int n, uint32_t* out) {
-    for (int i = 0; i < KW; i++) out[i] = 0;
-    for (int i = 0; i < n && i < KW * 8; i++) {
-        const uint32_t k = keys[i] <= 10 ? keys[i] : 0u;
-        out[i >> 3] |= k << (4 * (i & 7));
+#pragma unroll
+    for (int j = 0; j < KW; j++) {   // static word / nibble indices only (out[] stays in registers)
+        uint32_t w = 0;
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const int i = 8 * j + b;
+            if (i < n) {
+                const uint32_t k = keys[i];
+                w |= (k <= 10u ? k : 0u) << (4 * b);
+            }
+        }
+        out[j] = w;
     }
 }
 template <int KW> B2T_HD int packed_len(const uint32_t* w) {  // sequences hold no zero token except the null action

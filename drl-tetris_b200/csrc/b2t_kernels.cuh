@@ -12,6 +12,9 @@
 
 namespace b2t {
 
+#ifndef B2T_GAME_MINB
+#define B2T_GAME_MINB 4   // resident blocks per SM the step/expand kernel is register-capped for
+#endif
 constexpr int TPB = 128;
 constexpr int WARPS = TPB / 32;
 constexpr int STAT_SLICES = 64;
@@ -126,8 +129,11 @@ __device__ __forceinline__ void emit_fields(uint32_t* wb, const Board<G, TPB>& b
         if (byte0 + 16 <= valid_bytes) {
             *reinterpret_cast<uint4*>(out + byte0) = q;
         } else {
-            const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
-            for (int k = 0; byte0 + k < valid_bytes; k++) out[byte0 + k] = (uint8_t)(qq[k >> 2] >> (8 * (k & 3)));
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const uint32_t word = (k < 4) ? q.x : (k < 8) ? q.y : (k < 12) ? q.z : q.w;
+                if (byte0 + k < valid_bytes) out[byte0 + k] = (uint8_t)(word >> (8 * (k & 3)));
+            }
         }
     }
     __syncwarp();
@@ -160,9 +166,14 @@ __device__ __forceinline__ uint32_t squeeze_keys(uint32_t w) {
     return x;
 }
 
+// 4 packed tokens (16 bits) -> 4 key bytes
+__device__ __forceinline__ uint32_t spread_nibbles(uint32_t x) {
+    return (x & 0xFu) | ((x & 0xF0u) << 4) | ((x & 0xF00u) << 8) | ((x & 0xF000u) << 12);
+}
+
 // ---------------------------------------------------------------------------------------------- the game kernel
 template <class G>
-__global__ void __launch_bounds__(TPB) game_kernel(const KParams p) {
+__global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams p) {
     typedef typename G::col_t col_t;
     typedef SmemLayout<G> L;
     constexpr int KW = G::KEYW;
@@ -228,7 +239,9 @@ __global__ void __launch_bounds__(TPB) game_kernel(const KParams p) {
         if (p.flags & KF_POKE_DEAD) {
             if (p.poke_player == 0) g.p[0].dead = p.poke_value; else g.p[1].dead = p.poke_value;
         }
-        if (p.flags & KF_CLEAR_FIELD) board_clear<G, TPB>(p.poke_player ? g.b[1] : g.b[0]);
+        if (p.flags & KF_CLEAR_FIELD) {
+            if (p.poke_player == 0) board_clear<G, TPB>(g.b[0]); else board_clear<G, TPB>(g.b[1]);
+        }
         if (p.flags & (KF_STEP | KF_EXPAND)) {
             const int player = p.player[i] ? 1 : 0;
             uint32_t kw[KW];
@@ -277,7 +290,24 @@ __global__ void __launch_bounds__(TPB) game_kernel(const KParams p) {
                 if (p.key_len_out) p.key_len_out[row] = (uint8_t)nkeys;
                 if (p.keys_out) {
                     uint8_t* ko = p.keys_out + (size_t)row * (size_t)p.lmax_out;
-                    for (int j = 0; j < p.lmax_out; j++) ko[j] = (j < KW * 8) ? (uint8_t)((kw[j >> 3] >> (4 * (j & 7))) & 15u) : 0;
+                    const bool vec_ok = (p.lmax_out & 15) == 0 && (reinterpret_cast<uintptr_t>(p.keys_out) & 15) == 0;
+#pragma unroll
+                    for (int c = 0; c < KW / 2; c++) {          // 16 keys (two packed words) per 128-bit store
+                        if (16 * c < p.lmax_out) {
+                            uint4 q;
+                            q.x = spread_nibbles(kw[2 * c] & 0xFFFFu); q.y = spread_nibbles(kw[2 * c] >> 16);
+                            q.z = spread_nibbles(kw[2 * c + 1] & 0xFFFFu); q.w = spread_nibbles(kw[2 * c + 1] >> 16);
+                            if (vec_ok) *reinterpret_cast<uint4*>(ko + 16 * c) = q;
+                            else {
+#pragma unroll
+                                for (int b = 0; b < 16; b++) {
+                                    const uint32_t word = (b < 4) ? q.x : (b < 8) ? q.y : (b < 12) ? q.z : q.w;
+                                    if (16 * c + b < p.lmax_out) ko[16 * c + b] = (uint8_t)(word >> (8 * (b & 3)));
+                                }
+                            }
+                        }
+                    }
+                    for (int j = KW * 8; j < p.lmax_out; j++) ko[j] = 0;
                 }
             } else if (finalize && !was_over) {
                 st_steps = 1;
