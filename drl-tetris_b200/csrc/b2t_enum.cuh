@@ -12,6 +12,13 @@
 #pragma once
 #include "b2t_core.cuh"
 
+#if defined(B2T_COUNTERS) && !defined(__CUDA_ARCH__)
+extern "C" long long b2t_counters[16];   // test-only instrumentation (tests/hostsim): 0 boards 1 candidates 2 reachable 3 fits in search
+#define B2T_COUNT(i) (++b2t_counters[i])
+#else
+#define B2T_COUNT(i) do { } while (0)
+#endif
+
 namespace b2t {
 
 template <int KW> struct Seq {
@@ -43,6 +50,15 @@ template <int KW> struct Seq {
         return t;
     }
 };
+
+// [rotation][|x - spawn| laterals][7] as one 64-bit token string (<= 16 tokens: W <= 32), TestField.cpp:113-121
+B2T_HD uint64_t top_drop_tokens(int rot_delta, int dx) {
+    const int an = dx < 0 ? -dx : dx;
+    uint64_t s = (dx > 0 ? 0x3333333333333333ull : 0x1111111111111111ull) & ((1ull << (4 * an)) - 1ull);
+    s |= 7ull << (4 * an);
+    if (rot_delta) s = (s << 4) | (uint64_t)(rot_delta == 1 ? 8u : rot_delta == 2 ? 10u : 9u);
+    return s;
+}
 
 template <int KW> B2T_HD bool seq_equal(const Seq<KW>& a, const uint32_t* b) {
     bool eq = true;
@@ -81,7 +97,7 @@ template <class G, int S, int KW, class Sink> struct Enumerator {
     }
     B2T_HD uint32_t pcn(int r) const { return (uint32_t)(pcn4 >> (16 * r)) & 0xFFFFu; }
     B2T_HD uint32_t pcc(int r) const { return (uint32_t)(pcc4 >> (16 * r)) & 0xFFFFu; }
-    B2T_HD bool fit_at(int xx, int yy, int rr) const { return fits<G, S>(b, xx, yy, pcn(rr)); }
+    B2T_HD bool fit_at(int xx, int yy, int rr) const { B2T_COUNT(3); return fits<G, S>(b, xx, yy, pcn(rr)); }
     B2T_HD bool fit() const { return fit_at(x, y, rot); }
 
     // ---- test_path bookkeeping
@@ -242,22 +258,31 @@ template <class G, int S, int KW, class Sink> struct Enumerator {
     }
     B2T_HD void emit_top(int r, int xx) {
         Seq<KW> s; s.clear();
-        emit_prefix(s, r, xx);
-        s.push(7u);
+        const int dx = xx - G::SPAWN_X;
+        const uint64_t t = top_drop_tokens((r - spawn_rot) & 3, dx);
+        s.w[0] = (uint32_t)t; s.w[1] = (uint32_t)(t >> 32);
+        s.n = (dx < 0 ? -dx : dx) + 1 + (((r - spawn_rot) & 3) ? 1 : 0);
         sink.top(s, false);
     }
-    B2T_HD void emit_finesse() {
-        Seq<KW> s; s.clear();
+    // forward key sequence of the recorded finesse move (useFinesseMove, :127-164); returns true if it did not fit
+    B2T_HD bool build_finesse(Seq<KW>& s) const {
+        s.clear();
         emit_prefix(s, best_rot, best_x);
         Seq<KW> p = best;
-        bool bad = best_bad || (s.n + p.n + 1 > KW * 8);
+        const bool bad = best_bad || (s.n + p.n + 1 > KW * 8);
         while (p.n > 0 && s.n < KW * 8 - 1) s.push(p.pop_front());
         s.push(7u);
+        return bad;
+    }
+    B2T_HD void emit_finesse() {
+        Seq<KW> s;
+        const bool bad = build_finesse(s);
         sink.finesse(s, bad);
     }
 
     // getMask (:64-111) + findNextMove (:113-125) + tryAllFinesseMoves (:174-187)
     B2T_HD void run(int cur_rot) {
+        B2T_COUNT(0);
         const int nrot = (kind == 6) ? 1 : (kind == 4 || kind == 2 || kind == 3) ? 2 : 4;
         for (int xx = -1; xx < G::W - 1; xx++)
             for (int r0 = 0; r0 < nrot; r0++) {
@@ -274,7 +299,8 @@ template <class G, int S, int KW, class Sink> struct Enumerator {
                     const int a = yy + ctz(free_);
                     const int rest = rest_from<G>(cm, a);
                     x = xx; y = rest; rot = r;
-                    if (reachable()) emit_finesse();
+                    B2T_COUNT(1);
+                    if (reachable()) { B2T_COUNT(2); emit_finesse(); }
                     yy = rest + 1;
                 }
             }

@@ -83,7 +83,6 @@ template <class G> struct SmemLayout {
     static constexpr int VEC = WARPS * 32 * 2 * VEC_LEN;
     static constexpr int TAB = 64 * 2;
     static constexpr int GAME_TOTAL = COLS + STREAM + BITS + ((VEC + 15) / 16) * 16 + TAB;
-    static constexpr int ENUM_TOTAL = G::NCOL * TPB * (int)sizeof(col_t) + TAB;
 };
 
 // ---------------------------------------------------------------------------------------------- cooperative outputs
@@ -382,47 +381,54 @@ struct EParams {
     DevTabs tabs;
 };
 
-template <int KW> struct DevSink {
-    uint32_t* out;
-    int cap, count, bad, first_fin;
-    __device__ __forceinline__ void put(int slot, const Seq<KW>& s) {
-        uint4* o = reinterpret_cast<uint4*>(out + (size_t)slot * KW);
-#pragma unroll
-        for (int j = 0; j < KW / 4; j++) o[j] = make_uint4(s.w[4 * j], s.w[4 * j + 1], s.w[4 * j + 2], s.w[4 * j + 3]);
-    }
-    __device__ __forceinline__ void top(const Seq<KW>& s, bool b) {
-        if (b) bad = 1;
-        if (count < cap) put(count, s); else bad = 1;
-        count++;
-    }
-    __device__ __forceinline__ void finesse(const Seq<KW>& s, bool b) {
-        // action_list.py:14 — first occurrence wins.  Only under-overhang sequences can repeat each other
-        // (a top drop never contains a 5/6 or a late rotation), so compare from the first finesse entry on.
-        if (first_fin >= 0) {
-            const int lim = count < cap ? count : cap;
-            for (int k = first_fin; k < lim; k++) {
-                const uint4* o = reinterpret_cast<const uint4*>(out + (size_t)k * KW);
-                bool eq = true;
-#pragma unroll
-                for (int j = 0; j < KW / 4; j++) {
-                    const uint4 q = o[j];
-                    eq = eq && q.x == s.w[4 * j] && q.y == s.w[4 * j + 1] && q.z == s.w[4 * j + 2] && q.w == s.w[4 * j + 3];
-                }
-                if (eq) return;
-            }
-        } else first_fin = count;
-        top(s, b);
-    }
+// Placement enumeration, one board per thread, in three phases so that the rare, expensive under-overhang search never
+// runs with one lane active while 31 wait:
+//   1. (converged) every lane scans a chunk of (column, rotation) combos of ITS board: one collision mask per combo gives
+//      the top drop (a bit in `topmask`) and the resting heights of the cavities below it (candidates, in shared memory);
+//   2. (pooled) the warp's candidates are dealt out evenly to the 32 lanes, each runs the backward search on the OWNER's
+//      board (boards are in shared memory), results return through a per-warp buffer, and each owner accepts its results
+//      in candidate order (first-occurrence de-duplication, action_list.py:14) straight into their final list slots:
+//      slot = #top drops with combo <= c  +  #finesse entries accepted before;
+//   3. every lane writes its top drops into the remaining slots.
+// Emission order is exactly TestField::getMask's: combos ascending (x-major, rotation-minor), top drop first, then the
+// combo's cavities by increasing height.
+template <class G> struct EnumCfg {
+    static constexpr int CCAP = 64;                                  // candidate slots per thread per chunk
+    static constexpr int PER_COMBO = (G::H - 1) / 2;                 // resting heights differ by >= 2 and start at 2
+    static constexpr int CH = (CCAP / PER_COMBO) < 1 ? 1 : (CCAP / PER_COMBO);   // combos per chunk (never overflows CCAP)
+    static constexpr int NCOMBO = 4 * G::W;
+    static constexpr int NCHUNK = (NCOMBO + CH - 1) / CH;
+    static constexpr int ACAP = G::KMAX;                             // accepted finesse entries per board (cannot overflow before the list does)
+    static_assert(NCOMBO <= 128, "topmask is 128 bits");
+    static constexpr int SMEM = G::NCOL * TPB * (int)sizeof(typename G::col_t) + CCAP * TPB * 2 + ACAP * TPB + TPB * 16 +
+                                WARPS * 32 * G::KEYW * 4 + 128;
 };
+
+struct NoSink {
+    template <class S> B2T_HD void top(const S&, bool) {}
+    template <class S> B2T_HD void finesse(const S&, bool) {}
+};
+
+__device__ __forceinline__ int rank128(uint64_t lo, uint64_t hi, int nbits) {  // set bits among the lowest nbits (0..128)
+    if (nbits <= 0) return 0;
+    if (nbits >= 128) return __popcll(lo) + __popcll(hi);
+    if (nbits <= 64) return __popcll(nbits == 64 ? lo : (lo & ((1ull << nbits) - 1ull)));
+    return __popcll(lo) + __popcll(hi & ((1ull << (nbits - 64)) - 1ull));
+}
 
 template <class G>
 __global__ void __launch_bounds__(TPB) enumerate_kernel(const EParams p) {
     typedef typename G::col_t col_t;
+    typedef EnumCfg<G> C;
     constexpr int KW = G::KEYW;
     extern __shared__ __align__(16) unsigned char smem[];
     col_t* s_cols = reinterpret_cast<col_t*>(smem);
-    uint16_t* s_tab = reinterpret_cast<uint16_t*>(smem + G::NCOL * TPB * sizeof(col_t));
-    const int tid = threadIdx.x;
+    uint16_t* s_cand = reinterpret_cast<uint16_t*>(smem + G::NCOL * TPB * sizeof(col_t));        // [CCAP][TPB]
+    uint8_t* s_acc = reinterpret_cast<uint8_t*>(s_cand + C::CCAP * TPB);                           // [ACAP][TPB] combo of accepted entry
+    uint64_t* s_pc4 = reinterpret_cast<uint64_t*>(s_acc + C::ACAP * TPB);                          // [TPB][2] pcn4, pcc4 of the owner's piece
+    uint32_t* s_res = reinterpret_cast<uint32_t*>(s_pc4 + 2 * TPB);                                // [WARPS][32][KW]
+    uint16_t* s_tab = reinterpret_cast<uint16_t*>(s_res + WARPS * 32 * KW);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i = blockIdx.x * TPB + tid;
     if (tid < 28) { s_tab[tid] = p.tabs.pcn[tid]; s_tab[32 + tid] = p.tabs.pcc[tid]; }
     Tabs tb;
@@ -434,35 +440,169 @@ __global__ void __launch_bounds__(TPB) enumerate_kernel(const EParams p) {
     b.stream = nullptr;
     board_init_walls<G, TPB>(b);
     __syncthreads();
-    if (i >= p.n) return;
-    const int gi = p.idx ? p.idx[i] : i;
-    const int pl = p.player[i] ? 1 : 0;
-    const uint32_t* words = reinterpret_cast<const uint32_t*>(p.state);
-    auto word = [&](int wi) { return words[((size_t)(wi >> 2) * (size_t)p.n_games + (size_t)gi) * 4 + (wi & 3)]; };
-    const int base = pl * G::PW;
-    for (int c = 0; c < G::W; c++) {
-        if (G::CW == 1) b.col(c) = (col_t)word(base + c);
-        else b.col(c) = (col_t)((uint64_t)word(base + 2 * c) | ((uint64_t)word(base + 2 * c + 1) << 32));
+    const bool active = i < p.n;
+    int gi = 0, kind = 7, cur_rot = 0;
+    if (active) {
+        gi = p.idx ? p.idx[i] : i;
+        const int pl = p.player[i] ? 1 : 0;
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(p.state);
+        auto word = [&](int wi) { return words[((size_t)(wi >> 2) * (size_t)p.n_games + (size_t)gi) * 4 + (wi & 3)]; };
+        const int base = pl * G::PW;
+        for (int c = 0; c < G::W; c++) {
+            if (G::CW == 1) b.col(c) = (col_t)word(base + c);
+            else b.col(c) = (col_t)((uint64_t)word(base + 2 * c) | ((uint64_t)word(base + 2 * c + 1) << 32));
+        }
+        const uint32_t w0 = word(base + G::W * G::CW + G::SW);
+        kind = w0 & 7; cur_rot = (w0 >> 3) & 3;
     }
-    const uint32_t w0 = word(base + G::W * G::CW + G::SW);
-    const int kind = w0 & 7, rot = (w0 >> 3) & 3;
-    DevSink<KW> sink;
+    const int kk = kind <= 6 ? kind : 0;
+    uint64_t pcn4 = 0, pcc4 = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        pcn4 |= (uint64_t)tb.pcn[kk * 4 + r] << (16 * r);
+        pcc4 |= (uint64_t)tb.pcc[kk * 4 + r] << (16 * r);
+    }
+    s_pc4[2 * tid] = pcn4; s_pc4[2 * tid + 1] = pcc4;
+    const int nrot = (kind > 6) ? 0 : (kind == 6) ? 1 : (kind == 4 || kind == 2 || kind == 3) ? 2 : 4;
+    const int spawn = spawn_rot_of(tb, kk);
     const int off = p.bar_null ? 0 : 1;
-    uint32_t* lst = p.plc + (size_t)gi * G::KMAX * KW;
-    sink.out = lst + off * KW; sink.cap = G::KMAX - off; sink.count = 0; sink.bad = 0; sink.first_fin = -1;
-    if (kind <= 6) {
-        Enumerator<G, TPB, KW, DevSink<KW>> e(b, tb, kind, sink);
-        e.run(rot);
+    uint32_t* lst = p.plc + (size_t)gi * G::KMAX * KW;      // this board's list (only dereferenced by active lanes)
+    uint64_t top_lo = 0, top_hi = 0;
+    int nacc = 0, bad = 0;
+    __syncwarp();
+
+    for (int chunk = 0; chunk < C::NCHUNK; chunk++) {
+        // ---- phase 1: my combos of this chunk
+        int ncand = 0;
+        for (int cc = 0; cc < C::CH; cc++) {
+            const int c = chunk * C::CH + cc;
+            const int r0 = c & 3, xx = (c >> 2) - 1;
+            if (c < C::NCOMBO && r0 < nrot) {
+                const int r = (kind == 6) ? cur_rot : r0;
+                const col_t cm = collide_mask<G, TPB>(b, xx, (uint32_t)(pcc4 >> (16 * r)) & 0xFFFFu);
+                if (!((cm >> G::YB) & 1)) {
+                    if (c < 64) top_lo |= 1ull << c; else top_hi |= 1ull << (c - 64);
+                    int yy = rest_from<G>(cm, 0) + 2;
+                    while (yy < G::H - 1) {
+                        col_t free_ = (col_t)(~cm >> (yy + G::YB));
+                        free_ &= (col_t)((G::one() << (G::H - 1 - yy)) - 1);
+                        if (!free_) break;
+                        const int rest = rest_from<G>(cm, yy + ctz(free_));
+                        if (ncand < C::CCAP) s_cand[ncand * TPB + tid] = (uint16_t)((c << 8) | (r << 6) | rest);
+                        else bad = 1;
+                        ncand++;
+                        yy = rest + 1;
+                    }
+                }
+            }
+        }
+        if (ncand > C::CCAP) ncand = C::CCAP;
+        // ---- phase 2: pool the warp's candidates
+        int incl = ncand;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        const int excl = incl - ncand;
+        __syncwarp();
+        for (int g0 = 0; g0 < total; g0 += 32) {
+            const int g = g0 + lane;
+            uint32_t* res = s_res + (warp * 32 + lane) * KW;
+            // owner = first lane whose inclusive count exceeds g
+            int o = 0;
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const int t = o + step;
+                const int v = __shfl_sync(0xFFFFFFFFu, incl, (t - 1) & 31);
+                if (t <= 31 && v <= g) o = t;
+            }
+            const int o_excl = __shfl_sync(0xFFFFFFFFu, excl, o);
+            const int o_kind = __shfl_sync(0xFFFFFFFFu, kind, o);
+            bool ok = false;
+            Seq<KW> seq;
+            seq.clear();
+            if (g < total) {
+                const int otid = warp * 32 + o;
+                const uint32_t cd = s_cand[(g - o_excl) * TPB + otid];
+                Board<G, TPB> ob;
+                ob.cols = s_cols + otid;
+                ob.stream = nullptr;
+                NoSink ns;
+                Enumerator<G, TPB, KW, NoSink> e(ob, tb, o_kind, ns);
+                e.pcn4 = s_pc4[2 * otid]; e.pcc4 = s_pc4[2 * otid + 1];
+                e.x = (int)(cd >> 10) - 1; e.y = (int)(cd & 63u); e.rot = (int)((cd >> 6) & 3u);
+                if (e.reachable()) {
+                    ok = true;
+                    if (e.build_finesse(seq)) seq.w[KW - 1] |= 0u;   // (overflow is reported by the owner below)
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < KW; j++) res[j] = ok ? seq.w[j] : 0u;
+            __syncwarp();
+            // ---- collect: I am the owner of round entries [a, bnd)
+            int a = excl - g0, bnd = incl - g0;
+            a = a < 0 ? 0 : a; bnd = bnd > 32 ? 32 : bnd;
+            for (int t = a; t < bnd; t++) {
+                const uint32_t* rr = s_res + (warp * 32 + t) * KW;
+                if (rr[0] == 0u) continue;
+                const int c = (int)(s_cand[(g0 + t - excl) * TPB + tid] >> 8);
+                bool dup = false;
+                for (int f = 0; f < nacc && !dup; f++) {
+                    const int fc = s_acc[f * TPB + tid];
+                    const int slot = off + rank128(top_lo, top_hi, fc + 1) + f;
+                    if (slot < G::KMAX) {
+                        const uint32_t* q = lst + (size_t)slot * KW;
+                        bool eq = true;
+#pragma unroll
+                        for (int j = 0; j < KW; j++) eq = eq && (q[j] == rr[j]);
+                        dup = eq;
+                    }
+                }
+                if (dup) continue;
+                const int slot = off + rank128(top_lo, top_hi, c + 1) + nacc;
+                if (slot < G::KMAX && nacc < C::ACAP) {
+                    uint4* dst = reinterpret_cast<uint4*>(lst + (size_t)slot * KW);
+#pragma unroll
+                    for (int j = 0; j < KW / 4; j++) dst[j] = make_uint4(rr[4 * j], rr[4 * j + 1], rr[4 * j + 2], rr[4 * j + 3]);
+                    s_acc[nacc * TPB + tid] = (uint8_t)c;
+                } else bad = 1;
+                nacc++;
+            }
+            __syncwarp();
+        }
     }
-    int K = sink.count + off;
-    if (sink.count == 0 || off) {   // null action [0] in slot 0 (action_list.py:6-12,18-20)
-        Seq<KW> z; z.clear();
-        sink.out = lst; sink.put(0, z);
-        if (sink.count == 0) K = 1;
+    // ---- phase 3: top drops
+    if (active) {
+        if (nacc > C::ACAP) nacc = C::ACAP;
+        int f = 0, ntop = 0;
+        for (int c = 0; c < C::NCOMBO; c++) {
+            const bool has = (c < 64) ? ((top_lo >> c) & 1ull) : ((top_hi >> (c - 64)) & 1ull);
+            if (!has) continue;
+            while (f < nacc && s_acc[f * TPB + tid] < c) f++;
+            const int slot = off + ntop + f;
+            const int r = (kind == 6) ? cur_rot : (c & 3);
+            const uint64_t t = top_drop_tokens((r - spawn) & 3, ((c >> 2) - 1) - G::SPAWN_X);
+            if (slot < G::KMAX) {
+                uint4* dst = reinterpret_cast<uint4*>(lst + (size_t)slot * KW);
+                dst[0] = make_uint4((uint32_t)t, (uint32_t)(t >> 32), 0u, 0u);
+#pragma unroll
+                for (int j = 1; j < KW / 4; j++) dst[j] = make_uint4(0u, 0u, 0u, 0u);
+            } else bad = 1;
+            ntop++;
+        }
+        int K = ntop + nacc + off;
+        if (ntop + nacc == 0 || off) {   // null action [0] in slot 0 (action_list.py:6-12,18-20)
+            uint4* dst = reinterpret_cast<uint4*>(lst);
+#pragma unroll
+            for (int j = 0; j < KW / 4; j++) dst[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (ntop + nacc == 0) K = 1;
+        }
+        p.kcache[gi] = K;
+        if (p.K) p.K[i] = K;
+        if (bad && p.stats) atomicAdd(&p.stats[(blockIdx.x % STAT_SLICES) * STAT_WORDS + 7], 1ull);  // list capacity exceeded
     }
-    p.kcache[gi] = K;
-    if (p.K) p.K[i] = K;
-    if (sink.bad && p.stats) atomicAdd(&p.stats[(blockIdx.x % STAT_SLICES) * STAT_WORDS + 7], 1ull);  // list/sequence capacity exceeded
 }
 
 // packed cache -> the u8 [n,kmax,lmax] / [n,kmax] arrays of the reference-shaped API
@@ -612,7 +752,7 @@ template <class G> struct Launch {
     static cudaError_t prepare() {
         cudaError_t e = cudaFuncSetAttribute(game_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::GAME_TOTAL);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(enumerate_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::ENUM_TOTAL);
+        e = cudaFuncSetAttribute(enumerate_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, EnumCfg<G>::SMEM);
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(init_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::COLS + L::STREAM);
     }
@@ -623,7 +763,7 @@ template <class G> struct Launch {
     }
     static cudaError_t enumerate(const EParams& p, cudaStream_t s) {
         if (p.n <= 0) return cudaSuccess;
-        enumerate_kernel<G><<<(p.n + TPB - 1) / TPB, TPB, L::ENUM_TOTAL, s>>>(p);
+        enumerate_kernel<G><<<(p.n + TPB - 1) / TPB, TPB, EnumCfg<G>::SMEM, s>>>(p);
         return cudaGetLastError();
     }
     static cudaError_t unpack(const uint32_t* plc, const int32_t* kc, const int32_t* idx, int n, int kmax, int lmax, uint8_t* keys,
@@ -638,7 +778,7 @@ template <class G> struct Launch {
         return cudaGetLastError();
     }
     static const GeomOps* ops() {
-        static const GeomOps o = {G::H, G::W, G::NV, G::KMAX, G::KEYW, G::LMAX, L::GAME_TOTAL, L::ENUM_TOTAL,
+        static const GeomOps o = {G::H, G::W, G::NV, G::KMAX, G::KEYW, G::LMAX, L::GAME_TOTAL, EnumCfg<G>::SMEM,
                                   &prepare, &game, &enumerate, &unpack, &init};
         return &o;
     }

@@ -13,6 +13,10 @@
 
 using namespace b2t;
 
+#ifdef B2T_COUNTERS
+extern "C" { long long b2t_counters[16] = {0}; }
+#endif
+
 struct HSBase {
     virtual ~HSBase() {}
     virtual void reset(const int32_t* idx, int n, const uint32_t* seeds) = 0;
