@@ -63,34 +63,45 @@ def sventon_keys(gids, t, lmax=32):
 
 
 class ClockSampler(threading.Thread):
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons sampled through NVML every ~0.5 ms (nvidia-smi is too slow for a region that lasts a
+    few milliseconds); summary() reports the samples that fall inside [t0, t1] (the timed region)."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu, [], False
+        self.gpu, self.rows, self.stop_flag, self.err = gpu, [], False, None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.gpu
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    pass
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag:
+                self.rows.append((time.perf_counter(), pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), int(reasons_fn(h))))
+                time.sleep(0.0005)
+        except Exception as e:  # NVML missing: report nothing rather than fail the bench
+            self.err = repr(e)
 
-    def summary(self):
+    def summary(self, t0, t1):
         self.stop_flag = True
-        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(self.rows)}
+        self.join(timeout=2)
+        inside = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
+        sm = [r[1] for r in inside]
+        mask = 0
+        for r in inside:
+            mask |= r[2]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": getattr(self, "max_mhz", None),
+                "reasons": sorted(k for k, v in self.BAD.items() if mask & v), "samples_in_timed_region": len([r for r in self.rows if t0 <= r[0] <= t1]),
+                "source": "NVML" if self.err is None else "unavailable: " + self.err}
 
 
 def measured_peak():
@@ -206,13 +217,13 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from b200tetris import Engine
+    from b200tetris import Engine, sharding
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = a.games
-    gids = np.arange(n, dtype=np.int64) + rank * n           # GLOBAL game ids: results do not depend on the sharding
+    gids = sharding.global_ids(n * world, rank, world)        # GLOBAL game ids: results do not depend on the sharding
     eng = Engine(n, H, W, device=local)
     R = 4                                                     # ring of pre-generated action / seed tensors
     keys_r, len_r, seed_r = [], [], []
@@ -240,14 +251,17 @@ def main():
     sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
     torch.cuda.synchronize()
+    time.sleep(0.01)
+    wall0 = time.perf_counter()
     ev[0].record()
     for t in range(a.steps):
         one_step(a.warmup + t)
         ev[t + 1].record()
     torch.cuda.synchronize()
+    wall1 = time.perf_counter()
     total_ms = ev[0].elapsed_time(ev[-1])
     per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.steps)]
-    clocks = sampler.summary()
+    clocks = sampler.summary(wall0, wall1)
     tmax = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.barrier()
@@ -257,7 +271,7 @@ def main():
     peak, peak_src = measured_peak()
     k_ms = float(np.mean(per_launch_ms))
     achieved = STEP_BYTES * n / (k_ms * 1e-3) / 1e9
-    stats = eng.stats()
+    stats = sharding.reduce_stats(eng.stats(), device=dev)    # the only collective: end-of-rollout episode counters
 
     out = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": total_ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
