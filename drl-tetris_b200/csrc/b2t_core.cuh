@@ -598,7 +598,8 @@ template <class G, int S> B2T_HD int delay_check(PS& s, const Board<G, S>& b, co
 }
 
 // ---- keys (PythonHandle.cpp:73-112) and rotation with kicks (gameField.cpp:55-103)
-template <class G, int S> B2T_HD void rotate_key(PS& s, const Board<G, S>& b, const Tabs& tb, int turn) {
+// pcn = column nibbles of the piece at its current rotation, kept in a register across keys
+template <class G, int S> B2T_HD void rotate_key(PS& s, const Board<G, S>& b, const Tabs& tb, int turn, uint32_t& pcn_cur) {
     const int nr = (s.rot + turn) & 3;
     const uint32_t pcn = pcn_of(tb, s.kind, nr);
     int x = s.x, y = s.y;
@@ -606,35 +607,50 @@ template <class G, int S> B2T_HD void rotate_key(PS& s, const Board<G, S>& b, co
     if (!ok) {
         // kickTest walks these offsets cumulatively: (dy,dx) = (1,0)(0,-1)(0,1)(1,-1)(1,1)(0,-2)(0,2);
         // when all fail the reference undoes the net (+2,0) shift and the rotation (gameField.cpp:62-64)
-#pragma unroll
-        for (int k = 0; k < 7; k++) {
-            const int dy = (k == 0 || k == 3 || k == 4) ? 1 : 0;
-            const int dx = (k == 1 || k == 3) ? -1 : (k == 2 || k == 4) ? 1 : (k == 5) ? -2 : (k == 6) ? 2 : 0;
-            if (!ok && fits<G, S>(b, s.x + dx, s.y + dy, pcn)) { ok = true; x = s.x + dx; y = s.y + dy; }
+        for (int k = 0; k < 7 && !ok; k++) {
+            const int dy = (0x19 >> k) & 1;                          // dy = 1 for k = 0,3,4
+            const int dx = (int)((0x1032CAu >> (3 * k)) & 7u) - 2;   // dx+2 = 2,1,3,1,3,0,4 packed 3 bits each
+            if (fits<G, S>(b, s.x + dx, s.y + dy, pcn)) { ok = true; x = s.x + dx; y = s.y + dy; }
         }
     }
-    if (ok) { s.rot = nr; s.x = x; s.y = y; }
+    if (ok) { s.rot = nr; s.x = x; s.y = y; pcn_cur = pcn; }
 }
-template <class G, int S> B2T_HD void apply_key(PS& s, const Board<G, S>& b, const Tabs& tb, int key) {
-    if (s.kind > 6) return;
-    switch (key) {
-    case 1: case 3: {
-        const int dx = key == 1 ? -1 : 1;
-        if (fits<G, S>(b, s.x + dx, s.y, pcn_of(tb, s.kind, s.rot))) s.x += dx;
-    } break;
-    case 2: case 4: {
-        const int dx = key == 2 ? -1 : 1;
-        const uint32_t pcn = pcn_of(tb, s.kind, s.rot);
+template <class G, int S> B2T_HD void apply_key(PS& s, const Board<G, S>& b, const Tabs& tb, int key, uint32_t& pcn) {
+    if (key == 1 || key == 3) {
+        const int dx = key - 2;
+        if (fits<G, S>(b, s.x + dx, s.y, pcn)) s.x += dx;
+    } else if (key == 2 || key == 4) {
+        const int dx = key - 3;
         while (fits<G, S>(b, s.x + dx, s.y, pcn)) s.x += dx;
-    } break;
-    case 5: gp_move_down<G, S>(s, b, tb); break;
-    case 6: while (gp_move_down<G, S>(s, b, tb)) {} break;
-    case 7: hd_make<G, S>(s, b, tb); break;
-    case 8: rotate_key<G, S>(s, b, tb, 1); break;
-    case 9: rotate_key<G, S>(s, b, tb, 3); break;
-    case 10: rotate_key<G, S>(s, b, tb, 2); break;
-    default: break;
+    } else if (key == 5 || key == 6) {          // GamePlay::mDown once / until blocked, with its DropDelay bookkeeping
+        bool moved;
+        do {
+            moved = fits<G, S>(b, s.x, s.y + 1, pcn);
+            if (moved) { s.y++; dd_reset(s, s.time_ms); } else dd_set(s, s.time_ms);
+        } while (moved && key == 6);
+    } else if (key >= 8 && key <= 10) {
+        rotate_key<G, S>(s, b, tb, key == 8 ? 1 : key == 9 ? 3 : 2, pcn);
+    } else if (key == 7) {
+        hd_make<G, S>(s, b, tb);
     }
+}
+// The acting player's whole key string (4-bit tokens, word j at keys[j*KS]).  Every enumerated placement ends with the hard
+// drop; it is peeled off the loop so that all lanes of a warp lock their piece together instead of once per distinct length.
+template <class G, int S, int KS>
+B2T_HD void apply_keys(PS& s, const Board<G, S>& b, const Tabs& tb, const uint32_t* keys, int nkeys) {
+    if (s.kind > 6 || nkeys <= 0) return;
+    uint32_t pcn = pcn_of(tb, s.kind, s.rot);
+    const int last = nkeys - 1;
+    const bool final_drop = ((keys[(last >> 3) * KS] >> (4 * (last & 7))) & 15u) == 7u;
+    const int nloop = final_drop ? last : nkeys;
+    uint32_t cur = 0;
+    for (int i = 0; i < nloop; i++) {
+        if ((i & 7) == 0) cur = keys[(i >> 3) * KS];
+        const int key = (int)(cur & 15u);
+        cur >>= 4;
+        apply_key<G, S>(s, b, tb, key, pcn);
+    }
+    if (final_drop) hd_make<G, S>(s, b, tb);
 }
 
 // ---- PythonHandle.cpp:149-188 finish_actions for the 2-player game. gf = game flags. Returns round_over.

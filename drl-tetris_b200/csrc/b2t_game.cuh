@@ -51,8 +51,8 @@ template <class G, int S> B2T_HD void game_init(Game<G, S>& g) {
 }
 
 // tetris_environment.perform_action (tetris_environment.py:102-116) on one game.
-//   keys: packed 4-bit tokens, nkeys of them.  Returns env.done; *reward = reward_fcn base term.
-template <class G, int S, int KW>
+//   keys: packed 4-bit tokens (word j at keys[j*KS]), nkeys of them.  Returns env.done; *reward = reward_fcn base term.
+template <class G, int S, int KS>
 B2T_HD bool game_perform(Game<G, S>& g, const Tabs& tb, int player, const uint32_t* keys, int nkeys, bool finalize, int elapsed,
                          int* reward) {
     int gf = g.gf();
@@ -75,16 +75,7 @@ B2T_HD bool game_perform(Game<G, S>& g, const Tabs& tb, int player, const uint32
         bb.cols = one ? g.b[1].cols : g.b[0].cols;
         bb.stream = one ? g.b[1].stream : g.b[0].stream;
         if (!dead) {
-            uint32_t kw[KW];
-#pragma unroll
-            for (int i = 0; i < KW; i++) kw[i] = keys[i];
-            for (int i = 0; i < nkeys; i++) {
-                const int key = (int)(kw[0] & 15u);
-#pragma unroll
-                for (int j = 0; j + 1 < KW; j++) kw[j] = (kw[j] >> 4) | (kw[j + 1] << 28);
-                kw[KW - 1] >>= 4;
-                apply_key<G, S>(me, bb, tb, key);
-            }
+            apply_keys<G, S, KS>(me, bb, tb, keys, nkeys);
 #pragma unroll
             for (int q = 0; q < 2; q++)
                 if ((q == 1) == one) {

@@ -82,7 +82,9 @@ template <class G> struct SmemLayout {
     static constexpr int BITS = WARPS * (WB + 1) * 4;
     static constexpr int VEC = WARPS * 32 * 2 * VEC_LEN;
     static constexpr int TAB = 64 * 2;
-    static constexpr int GAME_TOTAL = COLS + STREAM + BITS + ((VEC + 15) / 16) * 16 + TAB;
+    static constexpr int KEYS = G::KEYW * TPB * 4;            // the acting player's packed key string, word j at [j][tid]
+    static constexpr int VEC16 = ((VEC + 15) / 16) * 16;
+    static constexpr int GAME_TOTAL = COLS + STREAM + BITS + VEC16 + KEYS + TAB;
 };
 
 // ---------------------------------------------------------------------------------------------- cooperative outputs
@@ -138,21 +140,47 @@ __device__ __forceinline__ void emit_fields(uint32_t* wb, const Board<G, TPB>& b
     __syncwarp();
 }
 
+// state_dict vector part (state_processors.py:33-41) of one player as 19 bytes in 5 words, built arithmetically:
+// [x y inc ct] [cc n0 n1 n2] [n3..n6] [k0..k3] [k4 k5 k6]
+__device__ __forceinline__ void vec_words(const PS& s, uint32_t* w) {
+    const uint32_t ct = (uint32_t)(s.remaining + 50) & 0xFFFFu;
+    const uint32_t ctp = (ct < 25000u ? ct : 25000u) / 100u;
+    const uint64_t ohn = (s.next < 7) ? (1ull << (8 * s.next)) : 0ull;   // one-hot bytes
+    const uint64_t ohk = (s.kind < 7) ? (1ull << (8 * s.kind)) : 0ull;
+    w[0] = (uint32_t)(s.x & 255) | ((uint32_t)(s.y & 255) << 8) | ((uint32_t)(s.inc_count & 255) << 16) | (ctp << 24);
+    w[1] = (uint32_t)(s.combo_count & 255) | ((uint32_t)ohn << 8);
+    w[2] = (uint32_t)(ohn >> 24);
+    w[3] = (uint32_t)ohk;
+    w[4] = (uint32_t)(ohk >> 32);
+}
 __device__ __forceinline__ void emit_vecs(uint8_t* sv, const PS& p0, const PS& p1, bool has_row, uint8_t* out, int valid_rows, int lane) {
     if (has_row) {
-        uint8_t v[VEC_LEN];
-        observe_vec(p0, v);
+        uint32_t a[5], b[5], r[10];
+        vec_words(p0, a);
+        vec_words(p1, b);
+        // 38-byte record = a (19 bytes) ++ b (19 bytes): b starts 3 bytes into word 4
+        r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; r[3] = a[3];
+        r[4] = (a[4] & 0xFFFFFFu) | (b[0] << 24);
+        r[5] = (b[0] >> 8) | (b[1] << 24);
+        r[6] = (b[1] >> 8) | (b[2] << 24);
+        r[7] = (b[2] >> 8) | (b[3] << 24);
+        r[8] = (b[3] >> 8) | (b[4] << 24);
+        r[9] = (b[4] >> 8) & 0xFFFFu;
+        uint16_t* d16 = reinterpret_cast<uint16_t*>(sv + lane * 2 * VEC_LEN);   // 2-byte aligned (38*lane)
 #pragma unroll
-        for (int k = 0; k < VEC_LEN; k++) sv[lane * 2 * VEC_LEN + k] = v[k];
-        observe_vec(p1, v);
-#pragma unroll
-        for (int k = 0; k < VEC_LEN; k++) sv[lane * 2 * VEC_LEN + VEC_LEN + k] = v[k];
+        for (int k = 0; k < 19; k++) d16[k] = (uint16_t)(r[k >> 1] >> (16 * (k & 1)));
     }
     __syncwarp();
-    const uint16_t* s16 = reinterpret_cast<const uint16_t*>(sv);
-    uint16_t* o16 = reinterpret_cast<uint16_t*>(out);
-    const int valid = valid_rows * VEC_LEN;  // halfwords
-    for (int k = lane; k < valid; k += 32) o16[k] = s16[k];
+    if (valid_rows == 32) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(sv);
+        uint4* o4 = reinterpret_cast<uint4*>(out);
+        for (int k = lane; k < 32 * 2 * VEC_LEN / 16; k += 32) o4[k] = s4[k];
+    } else {
+        const uint16_t* s16 = reinterpret_cast<const uint16_t*>(sv);
+        uint16_t* o16 = reinterpret_cast<uint16_t*>(out);
+        const int valid = valid_rows * VEC_LEN;  // halfwords
+        for (int k = lane; k < valid; k += 32) o16[k] = s16[k];
+    }
     __syncwarp();
 }
 
@@ -181,9 +209,11 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
     uint32_t* s_stream = reinterpret_cast<uint32_t*>(smem + L::COLS);
     uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem + L::COLS + L::STREAM);
     uint8_t* s_vec = smem + L::COLS + L::STREAM + L::BITS;
-    uint16_t* s_tab = reinterpret_cast<uint16_t*>(smem + L::COLS + L::STREAM + L::BITS + ((L::VEC + 15) / 16) * 16);
+    uint32_t* s_keys = reinterpret_cast<uint32_t*>(smem + L::COLS + L::STREAM + L::BITS + L::VEC16);
+    uint16_t* s_tab = reinterpret_cast<uint16_t*>(smem + L::COLS + L::STREAM + L::BITS + L::VEC16 + L::KEYS);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t* kw = s_keys + tid;                             // kw[j * TPB]
     const int row = blockIdx.x * TPB + tid;
     if (tid < 28) { s_tab[tid] = p.tabs.pcn[tid]; s_tab[32 + tid] = p.tabs.pcc[tid]; }
     Tabs tb;
@@ -243,20 +273,24 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
         }
         if (p.flags & (KF_STEP | KF_EXPAND)) {
             const int player = p.player[i] ? 1 : 0;
-            uint32_t kw[KW];
             int nkeys;
             if (expand || p.placement) {
                 int sel = expand ? k : p.placement[i];
                 const int kc = p.kcache[gi];
                 const bool valid = sel >= 0 && sel < kc && sel < G::KMAX;   // out of range -> null action (action_list.py:27-33)
                 const uint4* src = reinterpret_cast<const uint4*>(p.plc + ((size_t)gi * G::KMAX + (valid ? sel : 0)) * KW);
+                nkeys = 1;
 #pragma unroll
                 for (int j = 0; j < KW / 4; j++) {
-                    const uint4 q = src[j];
-                    kw[4 * j] = valid ? q.x : 0u; kw[4 * j + 1] = valid ? q.y : 0u;
-                    kw[4 * j + 2] = valid ? q.z : 0u; kw[4 * j + 3] = valid ? q.w : 0u;
+                    uint4 q = src[j];
+                    if (!valid) q = make_uint4(0u, 0u, 0u, 0u);
+                    kw[(4 * j) * TPB] = q.x; kw[(4 * j + 1) * TPB] = q.y; kw[(4 * j + 2) * TPB] = q.z; kw[(4 * j + 3) * TPB] = q.w;
+                    // sequences hold no zero token (except the null action): length = position of the last non-zero nibble
+                    if (q.x) nkeys = (4 * j) * 8 + (msb32(q.x) >> 2) + 1;
+                    if (q.y) nkeys = (4 * j + 1) * 8 + (msb32(q.y) >> 2) + 1;
+                    if (q.z) nkeys = (4 * j + 2) * 8 + (msb32(q.z) >> 2) + 1;
+                    if (q.w) nkeys = (4 * j + 3) * 8 + (msb32(q.w) >> 2) + 1;
                 }
-                nkeys = packed_len<KW>(kw);
             } else {
                 nkeys = p.key_len[i];
                 if (nkeys > KW * 8) nkeys = KW * 8;
@@ -264,23 +298,26 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
                 const uint8_t* kp = p.keys + (size_t)i * (size_t)p.lmax;
                 if ((p.lmax & 15) == 0 && ((reinterpret_cast<uintptr_t>(p.keys) & 15) == 0)) {
 #pragma unroll
-                    for (int j = 0; j < KW; j++) kw[j] = 0u;
-#pragma unroll
                     for (int j = 0; j < KW / 2; j++) {       // 16 keys per uint4 -> two packed words
+                        uint32_t a = 0u, b = 0u;
                         if (16 * j < nkeys) {
                             const uint4 q = *reinterpret_cast<const uint4*>(kp + 16 * j);
-                            kw[2 * j] = squeeze_keys(q.x) | (squeeze_keys(q.y) << 16);
-                            kw[2 * j + 1] = squeeze_keys(q.z) | (squeeze_keys(q.w) << 16);
+                            a = squeeze_keys(q.x) | (squeeze_keys(q.y) << 16);
+                            b = squeeze_keys(q.z) | (squeeze_keys(q.w) << 16);
                         }
+                        kw[(2 * j) * TPB] = a; kw[(2 * j + 1) * TPB] = b;
                     }
                 } else {
-                    pack_keys<KW>(kp, nkeys, kw);
+                    uint32_t tmp[KW];
+                    pack_keys<KW>(kp, nkeys, tmp);
+#pragma unroll
+                    for (int j = 0; j < KW; j++) kw[j * TPB] = tmp[j];
                 }
             }
             const bool was_over = (g.gf() & GF_ROUND_OVER) != 0;
             const bool finalize = (p.flags & KF_FINALIZE) != 0;
             int rew;
-            const bool done = game_perform<G, TPB, KW>(g, tb, player, kw, nkeys, finalize, p.elapsed, &rew);
+            const bool done = game_perform<G, TPB, TPB>(g, tb, player, kw, nkeys, finalize, p.elapsed, &rew);
             if (p.reward) p.reward[row] = (int8_t)rew;
             if (p.done) p.done[row] = done ? 1 : 0;
             if (p.lines) *reinterpret_cast<uint16_t*>(p.lines + 2 * (size_t)row) = (uint16_t)((g.p[0].reward & 255) | ((g.p[1].reward & 255) << 8));
@@ -294,8 +331,9 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
                     for (int c = 0; c < KW / 2; c++) {          // 16 keys (two packed words) per 128-bit store
                         if (16 * c < p.lmax_out) {
                             uint4 q;
-                            q.x = spread_nibbles(kw[2 * c] & 0xFFFFu); q.y = spread_nibbles(kw[2 * c] >> 16);
-                            q.z = spread_nibbles(kw[2 * c + 1] & 0xFFFFu); q.w = spread_nibbles(kw[2 * c + 1] >> 16);
+                            const uint32_t k0 = kw[(2 * c) * TPB], k1 = kw[(2 * c + 1) * TPB];
+                            q.x = spread_nibbles(k0 & 0xFFFFu); q.y = spread_nibbles(k0 >> 16);
+                            q.z = spread_nibbles(k1 & 0xFFFFu); q.w = spread_nibbles(k1 >> 16);
                             if (vec_ok) *reinterpret_cast<uint4*>(ko + 16 * c) = q;
                             else {
 #pragma unroll

@@ -128,7 +128,7 @@ template <int H, int W> struct HS : HSBase {
             uint32_t kw[KW];
             pack_keys<KW>(keys + (size_t)i * lmax, key_len[i], kw);
             int r;
-            bool d = game_perform<G, 1, KW>(g, tb, player[i], kw, key_len[i], finalize != 0, time_ms, &r);
+            bool d = game_perform<G, 1, 1>(g, tb, player[i], kw, key_len[i], finalize != 0, time_ms, &r);
             if (reward) reward[i] = (int8_t)r;
             if (done) done[i] = d;
             if (lines) { lines[2 * i] = (uint8_t)g.p[0].reward; lines[2 * i + 1] = (uint8_t)g.p[1].reward; }
@@ -227,7 +227,7 @@ template <int H, int W> struct HS : HSBase {
                 unpack_seq(&lst[(size_t)a * KW], dst, &key_len[o], lmax);
                 load(g, gi);
                 int r;
-                bool d = game_perform<G, 1, KW>(g, tb, player[i], &lst[(size_t)a * KW], packed_len<KW>(&lst[(size_t)a * KW]), finalize != 0, time_ms, &r);
+                bool d = game_perform<G, 1, 1>(g, tb, player[i], &lst[(size_t)a * KW], packed_len<KW>(&lst[(size_t)a * KW]), finalize != 0, time_ms, &r);
                 if (reward) reward[o] = (int8_t)r;
                 if (done) done[o] = d;
                 if (lines) { lines[2 * o] = (uint8_t)g.p[0].reward; lines[2 * o + 1] = (uint8_t)g.p[1].reward; }
