@@ -70,7 +70,7 @@ template <int KW> B2T_HD bool seq_equal(const Seq<KW>& a, const uint32_t* b) {
 // Sink concept:  void top(const Seq<KW>&);  void finesse(const Seq<KW>&);   (overflowing sequences set .bad)
 template <class G, int S, int KW, class Sink> struct Enumerator {
     typedef typename G::col_t col_t;
-    const Board<G, S>& b;
+    Board<G, S> b;      // by value (two pointers): the kernel re-points it at the owner of each pooled candidate
     Sink& sink;
     int kind, spawn_rot;
     uint64_t pcn4, pcc4;   // the four rotations of this piece, 16 bits each
@@ -94,6 +94,10 @@ template <class G, int S, int KW, class Sink> struct Enumerator {
         path.clear(); best.clear();
         path_entries = 0; path_bad = best_bad = false;
         best_x = best_rot = 0; x = y = rot = 0;
+    }
+    // light re-targeting for pooled searches: another board / piece, tables already packed by the owner
+    B2T_HD void rebind(const Board<G, S>& b_, int kind_, int spawn_rot_, uint64_t pcn4_, uint64_t pcc4_) {
+        b = b_; kind = kind_; spawn_rot = spawn_rot_; pcn4 = pcn4_; pcc4 = pcc4_;
     }
     B2T_HD uint32_t pcn(int r) const { return (uint32_t)(pcn4 >> (16 * r)) & 0xFFFFu; }
     B2T_HD uint32_t pcc(int r) const { return (uint32_t)(pcc4 >> (16 * r)) & 0xFFFFu; }
@@ -127,126 +131,153 @@ template <class G, int S, int KW, class Sink> struct Enumerator {
         if (count && blocked_below) return 253;
         return count;
     }
-    B2T_HD bool try_left(bool clear) {  // :202-220
-        for (;;) {
-            if (!fit_at(x - 1, y, rot)) return false;
-            x--;
-            if (clear) path_clear();
-            path_lateral(true);
-            path_up(move_up());
-            if (y == 0) return record();
-            clear = false;
-        }
+    // ---------------------------------------------------------------------------------------------------------------
+    // finesseIsPossible (:189-200) and everything below it (reverseWallkick :261-278, doWallKick :280-356, r180KeepPos
+    // :358-390, tryUp :240-259, tryLeft/tryRight :202-238) as ONE state machine, so that 32 lanes searching 32 different
+    // cavities share every instruction of the expensive primitives: search_step() runs, in this order, at most one
+    // "8 poses around a base" test (the inverse wall-kick probe or the forward-rotation check) and at most one slide
+    // (lateral moves with the rise after each), whatever stage each lane is in.  The observable quirks are kept: the right
+    // slide starts where the failed left slide stopped (:196-199, :252-258), paths are cleared only where the reference
+    // clears them, an in-place fit of a rotated pose ends doWallKick whatever tryUp returns (:294-302).
+    enum { ST_SIDE, ST_WK_R, ST_FWD, ST_TU, ST_TU_R, ST_WK_L, ST_WK_RR, ST_WK_FAIL, ST_FINAL_L, ST_FINAL_R, ST_DONE };
+    int st, sx, sy, sr, bx, by, br, px, py, pr, rp, turn, up, attempt, inplace;
+    bool found;
+
+    B2T_HD void search_begin(int cx, int cy, int cr) {
+        sx = x = cx; sy = y = cy; sr = rot = cr;
+        st = (kind == 6) ? ST_FINAL_L : ST_SIDE;
+        found = false;
+        bx = by = br = px = py = pr = rp = turn = up = attempt = inplace = 0;
     }
-    B2T_HD bool try_right(bool clear) {  // :222-238
-        for (;;) {
-            if (!fit_at(x + 1, y, rot)) return false;
-            x++;
-            if (clear) path_clear();
-            path_lateral(false);
-            path_up(move_up());
-            if (y == 0) return record();
-            clear = false;
-        }
-    }
-    B2T_HD bool try_up(int turn) {  // :240-259
-        path_clear();
-        const int up = move_up();
-        path_turn(turn);
-        path_up(up);
-        if (y == 0) return record();
-        if (try_left(false)) return true;
-        path_clear();
-        path_turn(turn);
-        path_up(up);
-        return try_right(false);
-    }
-    // BasicField::rcw/rccw/r180 on the probe piece (gameField.cpp:55-103)
-    B2T_HD bool forward_rotate(int turn) {
-        const int nr = (rot + turn) & 3;
-        if (fit_at(x, y, nr)) { rot = nr; return true; }
+    // bit 0: fits at (bx0, by0, r); bit k+1: fits at the k-th kick offset.  The 7 offsets are those of kickTest
+    // (gameField.cpp:93-103), cumulative (dy,dx) = (1,0)(0,-1)(0,1)(1,-1)(1,1)(0,-2)(0,2); `inverse` negates dy (:304-310)
+    B2T_HD uint32_t fit8(int bx0, int by0, int r, bool inverse) const {
+        typedef typename G::col_t col_t;
+        B2T_COUNT(4);
+        B2T_CHECK_XY(bx0 - 2, by0 - 1); B2T_CHECK_XY(bx0 + 2, by0 + 1);
+        const uint32_t n = pcn(r);
+        const col_t* p = b.cols + (bx0 - 2 + G::XL) * S;
+        col_t c[8];
 #pragma unroll
-        for (int k = 0; k < 7; k++) {
-            const int dy = (k == 0 || k == 3 || k == 4) ? 1 : 0;
-            const int dx = (k == 1 || k == 3) ? -1 : (k == 2 || k == 4) ? 1 : (k == 5) ? -2 : (k == 6) ? 2 : 0;
-            if (fit_at(x + dx, y + dy, nr)) { x += dx; y += dy; rot = nr; return true; }
-        }
-        return false;
-    }
-    B2T_HD bool wall_kick() {  // doWallKick, :280-356
-        const int sx = x, sy = y, sr = rot;
-        int r;
-        bool working = false;
-        for (r = 0; r < 4; r++) {
-            working = true;
-            if (r == sr) { working = false; continue; }
-            rot = r;
-            if (fit()) {
-                const bool ok = try_up((sr - r) & 3);
-                x = sx; y = sy; rot = sr;
-                return ok;
-            }
-            // inverse kick offsets, cumulative (dy,dx): (-1,0)(0,-1)(0,1)(-1,-1)(-1,1)(0,-2)(0,2)
-            bool found = false;
+        for (int j = 0; j < 8; j++) c[j] = p[j * S];
+        const int s0 = by0 + G::YB, s1 = inverse ? s0 - 1 : s0 + 1;
+        uint32_t m = 0;
 #pragma unroll
-            for (int k = 0; k < 7; k++) {
-                const int dy = (k == 0 || k == 3 || k == 4) ? -1 : 0;
-                const int dx = (k == 1 || k == 3) ? -1 : (k == 2 || k == 4) ? 1 : (k == 5) ? -2 : (k == 6) ? 2 : 0;
-                if (!found && fit_at(sx + dx, sy + dy, r)) { found = true; x = sx + dx; y = sy + dy; }
-            }
-            if (found) break;
-            x = sx; y = sy;
-            working = false;
+        for (int k = 0; k < 8; k++) {
+            const int dx = (k == 0) ? 0 : (k == 2 || k == 4) ? -1 : (k == 3 || k == 5) ? 1 : (k == 6) ? -2 : (k == 7) ? 2 : 0;
+            const bool dyk = (k == 1 || k == 4 || k == 5);
+            const int sh = dyk ? s1 : s0;
+            col_t acc = (c[dx + 2] >> sh) & (col_t)(n & 15u);
+            acc |= (c[dx + 3] >> sh) & (col_t)((n >> 4) & 15u);
+            acc |= (c[dx + 4] >> sh) & (col_t)((n >> 8) & 15u);
+            acc |= (c[dx + 5] >> sh) & (col_t)((n >> 12) & 15u);
+            if (acc == 0) m |= 1u << k;
         }
-        if (!working) { x = sx; y = sy; rot = sr; return false; }
-        const int turn = (sr - r) & 3;
-        const int px = x, py = y, pr = rot;   // candidate pre-pose
-        forward_rotate(turn);
-        if (x != sx || y != sy) { x = sx; y = sy; rot = sr; return false; }
-        x = px; y = py; rot = pr;
-        if (try_up(turn)) { x = sx; y = sy; rot = sr; return true; }
-        x = px; y = py; rot = pr;
-        path_clear();
-        path_turn(turn);
-        if (try_left(false)) { x = sx; y = sy; rot = sr; return true; }
-        x = px; y = py; rot = pr;
-        if (path_entries > 1) { path_clear(); path_turn(turn); }
-        const bool ok = try_right(false);
-        x = sx; y = sy; rot = sr;
-        return ok;
+        return m;
     }
-    B2T_HD void flip_in_place() {  // r180KeepPos, :358-390 (I,Z shift one way, S the other)
-        rot = (rot + 2) & 3;
+    B2T_HD static int kick_dx(int k) { return (int)((0x1032CAu >> (3 * k)) & 7u) - 2; }   // k = 0..6
+    B2T_HD static int kick_dy(int k) { return (0x19 >> k) & 1; }
+    B2T_HD void flip_pose(int& fx, int& fy, int& fr) const {  // r180KeepPos, :358-390 (I,Z shift one way, S the other)
+        fr = (fr + 2) & 3;
         const int s = (kind == 2) ? -1 : 1;
-        if (rot == 0) x += s;
-        else if (rot == 1) y += s;
-        else if (rot == 2) x -= s;
-        else y -= s;
+        if (fr == 0) fx += s;
+        else if (fr == 1) fy += s;
+        else if (fr == 2) fx -= s;
+        else fy -= s;
     }
-    B2T_HD bool reverse_kick() {  // reverseWallkick, :261-278
-        if (kind == 6) return false;
-        if (fit_at(x + 1, y, rot)) return false;
-        if (fit_at(x - 1, y, rot)) return false;
-        const int sx = x, sy = y, sr = rot;
-        if (wall_kick()) { x = sx; y = sy; rot = sr; return true; }
-        bool ok = false;
-        if (kind == 2 || kind == 3 || kind == 4) {
-            flip_in_place();
-            ok = wall_kick();
+    // one iteration; true when the search is over (result in `found`; on success path/x/rot hold the recorded move)
+    B2T_HD bool search_step() {
+        // ---- cheap stage transitions
+        if (st == ST_SIDE) {                                   // reverseWallkick :262-266
+            const bool fr = fit_at(sx + 1, sy, sr), fl = fit_at(sx - 1, sy, sr);
+            if (fr || fl) st = ST_FINAL_L;
+            else { attempt = 0; bx = sx; by = sy; br = sr; rp = 0; st = ST_WK_R; }
         }
-        x = sx; y = sy; rot = sr;
-        return ok;
-    }
-    B2T_HD bool reachable() {  // finesseIsPossible, :189-200
-        const int sx = x, sy = y, sr = rot;
-        bool ok = reverse_kick();
-        if (!ok) {
+        if (st == ST_WK_FAIL) {
+            if (attempt == 0 && (kind == 2 || kind == 3 || kind == 4)) {   // :272-275
+                attempt = 1; bx = sx; by = sy; br = sr;
+                flip_pose(bx, by, br);
+                rp = 0; st = ST_WK_R;
+            } else st = ST_FINAL_L;
+        }
+        // ---- the 8-pose primitive
+        bool want8 = false, inv = true;
+        int fx = 0, fy = 0, fr8 = 0;
+        if (st == ST_WK_R) {
+            if (rp == br) rp++;
+            if (rp > 3) st = ST_WK_FAIL;
+            else { want8 = true; fx = bx; fy = by; fr8 = rp; inv = true; }
+        } else if (st == ST_FWD) { want8 = true; fx = px; fy = py; fr8 = br; inv = false; }
+        if (want8) {
+            const uint32_t m8 = fit8(fx, fy, fr8, inv);
+            if (st == ST_WK_R) {
+                turn = (br - rp) & 3;
+                if (m8 & 1u) { x = bx; y = by; rot = rp; inplace = 1; st = ST_TU; }                    // :294-302
+                else if (m8 >> 1) {                                                                     // :304-310
+                    const int k = ctz32(m8 >> 1);
+                    px = bx + kick_dx(k); py = by - kick_dy(k); pr = rp;
+                    st = ST_FWD;
+                    return false;
+                } else { rp++; return false; }
+            } else {                                                                                    // :323-333
+                bool good = m8 != 0;
+                if (good) {
+                    const int k = ctz32(m8);
+                    const int lx = px + (k ? kick_dx(k - 1) : 0), ly = py + (k ? kick_dy(k - 1) : 0);
+                    good = (lx == bx && ly == by);
+                }
+                if (!good) { st = ST_WK_FAIL; return false; }
+                x = px; y = py; rot = pr; inplace = 0; st = ST_TU;
+            }
+        }
+        // ---- the slide primitive
+        int dir = 0, on_fail = ST_DONE;
+        bool clear = false, rise_first = false;
+        if (st == ST_TU) {                  // tryUp :240-252
+            path_clear(); path_turn(turn);
+            dir = -1; rise_first = true; on_fail = ST_TU_R;
+        } else if (st == ST_TU_R) {         // tryUp :254-258 (from wherever the left slide stopped)
+            path_clear(); path_turn(turn); path_up(up);
+            dir = 1; on_fail = inplace ? ST_WK_FAIL : ST_WK_L;
+        } else if (st == ST_WK_L) {         // doWallKick :340-344
+            x = px; y = py; rot = pr;
+            path_clear(); path_turn(turn);
+            dir = -1; on_fail = ST_WK_RR;
+        } else if (st == ST_WK_RR) {        // doWallKick :346-352
+            x = px; y = py; rot = pr;
+            if (path_entries > 1) { path_clear(); path_turn(turn); }
+            dir = 1; on_fail = ST_WK_FAIL;
+        } else if (st == ST_FINAL_L) {      // finesseIsPossible :195-196
             x = sx; y = sy; rot = sr;
-            ok = try_left(true);
-            if (!ok) ok = try_right(true);   // NOT restored in between (:196-199)
+            dir = -1; clear = true; on_fail = ST_FINAL_R;
+        } else if (st == ST_FINAL_R) {      // finesseIsPossible :199 (not restored)
+            dir = 1; clear = true; on_fail = ST_DONE;
         }
+        if (dir != 0) {
+            bool success = false;
+            for (;;) {
+                if (!rise_first) {
+                    if (!fit_at(x + dir, y, rot)) break;
+                    x += dir;
+                    if (clear) { path_clear(); clear = false; }
+                    path_lateral(dir < 0);
+                }
+                const int u = move_up();
+                if (rise_first) up = u;
+                path_up(u);
+                rise_first = false;
+                if (y == 0) { success = true; break; }
+            }
+            if (success) { record(); found = true; st = ST_DONE; }
+            else st = on_fail;
+        }
+        return st == ST_DONE;
+    }
+    B2T_HD bool reachable() {
+        search_begin(x, y, rot);
+        while (!search_step()) {}
         x = sx; y = sy; rot = sr;
-        return ok;
+        return found;
     }
 
     // ---- emission (:37-49, :113-164)

@@ -55,6 +55,7 @@ struct KParams {
     int32_t elapsed;
     const uint32_t* reset_seeds;  // fused reset of finished games
     const int32_t* offsets;       // KF_EXPAND: [n+1]
+    const int32_t* row_board;     // KF_EXPAND: [capacity] board slot of every row (filled by scan_finish)
     int32_t capacity;
     int32_t poke_player, poke_value;
     // outputs (row-indexed)
@@ -93,47 +94,85 @@ template <class G>
 __device__ __forceinline__ void emit_fields(uint32_t* wb, const Board<G, TPB>& b0, const Board<G, TPB>& b1, bool has_row,
                                             uint8_t* out, int valid_rows, int lane) {
     constexpr int HW = G::H * G::W;
-    constexpr int WB = 2 * HW;
-    for (int w = lane; w < WB + 1; w += 32) wb[w] = 0u;
-    __syncwarp();
+    constexpr int REM = HW & 31;                 // valid bits in a player's last stream word (0 = all 32)
+    constexpr int RW = (2 * HW + 31) / 32;       // words of one row's record (player 0 bits, then player 1 bits)
+    // 1. this lane's 2*HW-bit record in registers
+    uint32_t rec[RW + 1];
+#pragma unroll
+    for (int j = 0; j <= RW; j++) rec[j] = 0u;
     if (has_row) {
 #pragma unroll
-        for (int pl = 0; pl < 2; pl++) {
-            const Board<G, TPB>& b = pl ? b1 : b0;
+        for (int j = 0; j < G::SW; j++) rec[j] = b0.sw(j);
 #pragma unroll
-            for (int w = 0; w < G::SW; w++) {
-                const uint32_t v = b.sw(w);
-                const int o = lane * 2 * HW + pl * HW + 32 * w;
-                if ((HW & 31) == 0) {
-                    wb[o >> 5] = v;
-                } else if (v) {
-                    const int sh = o & 31;
-                    atomicOr(&wb[o >> 5], v << sh);
-                    if (sh) atomicOr(&wb[(o >> 5) + 1], v >> (32 - sh));
-                }
+        for (int j = 0; j < G::SW; j++) {
+            const uint32_t v = b1.sw(j);
+            if (REM == 0) rec[G::SW + j] = v;
+            else {
+                rec[G::SW - 1 + j] |= v << REM;
+                if (G::SW + j <= RW) rec[G::SW + j] |= v >> (32 - REM);
             }
         }
     }
+    // 2. place it at bit lane*2*HW of the warp's stream: shift by sh, first/last words are shared with the neighbours
+    const int bit0 = lane * 2 * HW, wo = bit0 >> 5, sh = bit0 & 31;
+    const int nbit0 = bit0 + 2 * HW, nsh = nbit0 & 31, nidx = (nbit0 >> 5) - wo;   // next lane's first word, relative
+    uint32_t o[RW + 1];
+#pragma unroll
+    for (int j = 0; j <= RW; j++) o[j] = __funnelshift_l(j ? rec[j - 1] : 0u, rec[j], sh);   // (rec[j]:rec[j-1]) << sh, high word
+    const uint32_t from_next = __shfl_down_sync(0xFFFFFFFFu, o[0], 1);
+    const int first = sh ? 1 : 0;                       // my word 0 is written by the previous lane when shared
+    const int lastk = nidx - (nsh ? 0 : 1);
+#pragma unroll
+    for (int j = 0; j <= RW; j++) {
+        uint32_t v = o[j];
+        if (j == nidx && nsh && lane < 31) v |= from_next;
+        if (j >= first && j <= lastk) wb[wo + j] = v;
+    }
     __syncwarp();
-    const int valid_bytes = valid_rows * 2 * HW;
+    // 3. every lane expands 16 bits -> 16 bytes -> one 128-bit store
     const uint16_t* hb = reinterpret_cast<const uint16_t*>(wb);
     constexpr int NCH = 4 * HW;  // 16-byte chunks in 32 rows
-    for (int c = lane; c < NCH; c += 32) {
-        const int byte0 = 16 * c;
-        if (byte0 >= valid_bytes) break;
-        const uint32_t h = hb[c];
-        uint4 q;
-        q.x = ((h & 15u) * 0x00204081u) & 0x01010101u;
-        q.y = (((h >> 4) & 15u) * 0x00204081u) & 0x01010101u;
-        q.z = (((h >> 8) & 15u) * 0x00204081u) & 0x01010101u;
-        q.w = (((h >> 12) & 15u) * 0x00204081u) & 0x01010101u;
-        if (byte0 + 16 <= valid_bytes) {
-            *reinterpret_cast<uint4*>(out + byte0) = q;
-        } else {
+    if (valid_rows == 32) {
+        const uint16_t* hp = hb + lane;
+        uint4* op = reinterpret_cast<uint4*>(out) + lane;
+#pragma unroll 4
+        for (int it = 0; it < NCH / 32; it++) {
+            const uint32_t h = hp[it * 32];
+            uint4 q;
+            q.x = ((h & 15u) * 0x00204081u) & 0x01010101u;
+            q.y = (((h >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+            q.z = (((h >> 8) & 15u) * 0x00204081u) & 0x01010101u;
+            q.w = ((h >> 12) * 0x00204081u) & 0x01010101u;
+            op[it * 32] = q;
+        }
+        if ((NCH & 31) != 0 && lane < (NCH & 31)) {
+            const uint32_t h = hp[(NCH / 32) * 32];
+            uint4 q;
+            q.x = ((h & 15u) * 0x00204081u) & 0x01010101u;
+            q.y = (((h >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+            q.z = (((h >> 8) & 15u) * 0x00204081u) & 0x01010101u;
+            q.w = ((h >> 12) * 0x00204081u) & 0x01010101u;
+            op[(NCH / 32) * 32] = q;
+        }
+    } else {
+        const int valid_bytes = valid_rows * 2 * HW;
+        for (int c = lane; c < NCH; c += 32) {
+            const int byte0 = 16 * c;
+            if (byte0 >= valid_bytes) break;
+            const uint32_t h = hb[c];
+            uint4 q;
+            q.x = ((h & 15u) * 0x00204081u) & 0x01010101u;
+            q.y = (((h >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+            q.z = (((h >> 8) & 15u) * 0x00204081u) & 0x01010101u;
+            q.w = ((h >> 12) * 0x00204081u) & 0x01010101u;
+            if (byte0 + 16 <= valid_bytes) {
+                *reinterpret_cast<uint4*>(out + byte0) = q;
+            } else {
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                const uint32_t word = (k < 4) ? q.x : (k < 8) ? q.y : (k < 12) ? q.z : q.w;
-                if (byte0 + k < valid_bytes) out[byte0 + k] = (uint8_t)(word >> (8 * (k & 3)));
+                for (int kk = 0; kk < 16; kk++) {
+                    const uint32_t word = (kk < 4) ? q.x : (kk < 8) ? q.y : (kk < 12) ? q.z : q.w;
+                    if (byte0 + kk < valid_bytes) out[byte0 + kk] = (uint8_t)(word >> (8 * (kk & 3)));
+                }
             }
         }
     }
@@ -236,13 +275,8 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
         total_rows = p.offsets[p.n];
         if (total_rows > p.capacity) total_rows = p.capacity;
         if (row < total_rows) {
-            int lo = 0, hi = p.n;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (p.offsets[mid] <= row) lo = mid; else hi = mid;
-            }
-            i = lo;
-            k = row - p.offsets[lo];
+            i = p.row_board[row];
+            k = row - p.offsets[i];
         }
     }
     const bool active = row < total_rows;
@@ -322,7 +356,6 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
             if (p.done) p.done[row] = done ? 1 : 0;
             if (p.lines) *reinterpret_cast<uint16_t*>(p.lines + 2 * (size_t)row) = (uint16_t)((g.p[0].reward & 255) | ((g.p[1].reward & 255) << 8));
             if (expand) {
-                if (p.board_of) p.board_of[row] = i;
                 if (p.key_len_out) p.key_len_out[row] = (uint8_t)nkeys;
                 if (p.keys_out) {
                     uint8_t* ko = p.keys_out + (size_t)row * (size_t)p.lmax_out;
@@ -438,8 +471,9 @@ template <class G> struct EnumCfg {
     static constexpr int NCHUNK = (NCOMBO + CH - 1) / CH;
     static constexpr int ACAP = G::KMAX;                             // accepted finesse entries per board (cannot overflow before the list does)
     static_assert(NCOMBO <= 128, "topmask is 128 bits");
+    static constexpr int RES = 64;                                   // pooled results buffered per warp between acceptances
     static constexpr int SMEM = G::NCOL * TPB * (int)sizeof(typename G::col_t) + CCAP * TPB * 2 + ACAP * TPB + TPB * 16 +
-                                WARPS * 32 * G::KEYW * 4 + 128;
+                                WARPS * RES * G::KEYW * 4 + WARPS * 32 * 4 + WARPS * 4 + TPB * 4 + 128;
 };
 
 struct NoSink {
@@ -464,8 +498,11 @@ __global__ void __launch_bounds__(TPB) enumerate_kernel(const EParams p) {
     uint16_t* s_cand = reinterpret_cast<uint16_t*>(smem + G::NCOL * TPB * sizeof(col_t));        // [CCAP][TPB]
     uint8_t* s_acc = reinterpret_cast<uint8_t*>(s_cand + C::CCAP * TPB);                           // [ACAP][TPB] combo of accepted entry
     uint64_t* s_pc4 = reinterpret_cast<uint64_t*>(s_acc + C::ACAP * TPB);                          // [TPB][2] pcn4, pcc4 of the owner's piece
-    uint32_t* s_res = reinterpret_cast<uint32_t*>(s_pc4 + 2 * TPB);                                // [WARPS][32][KW]
-    uint16_t* s_tab = reinterpret_cast<uint16_t*>(s_res + WARPS * 32 * KW);
+    uint32_t* s_res = reinterpret_cast<uint32_t*>(s_pc4 + 2 * TPB);                                // [WARPS][RES][KW]
+    int* s_incl = reinterpret_cast<int*>(s_res + WARPS * C::RES * KW);                             // [WARPS][32] inclusive candidate counts
+    int* s_q = s_incl + WARPS * 32;                                                                // [WARPS] work-queue heads
+    int* s_kind = s_q + WARPS;                                                                     // [TPB] piece of every thread's board
+    uint16_t* s_tab = reinterpret_cast<uint16_t*>(s_kind + TPB);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i = blockIdx.x * TPB + tid;
     if (tid < 28) { s_tab[tid] = p.tabs.pcn[tid]; s_tab[32 + tid] = p.tabs.pcc[tid]; }
@@ -501,6 +538,7 @@ __global__ void __launch_bounds__(TPB) enumerate_kernel(const EParams p) {
         pcc4 |= (uint64_t)tb.pcc[kk * 4 + r] << (16 * r);
     }
     s_pc4[2 * tid] = pcn4; s_pc4[2 * tid + 1] = pcc4;
+    s_kind[tid] = kk;
     const int nrot = (kind > 6) ? 0 : (kind == 6) ? 1 : (kind == 4 || kind == 2 || kind == 3) ? 2 : 4;
     const int spawn = spawn_rot_of(tb, kk);
     const int off = p.bar_null ? 0 : 1;
@@ -544,46 +582,60 @@ __global__ void __launch_bounds__(TPB) enumerate_kernel(const EParams p) {
         }
         const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
         const int excl = incl - ncand;
+        s_incl[warp * 32 + lane] = incl;
         __syncwarp();
-        for (int g0 = 0; g0 < total; g0 += 32) {
-            const int g = g0 + lane;
-            uint32_t* res = s_res + (warp * 32 + lane) * KW;
-            // owner = first lane whose inclusive count exceeds g
-            int o = 0;
+        for (int g0 = 0; g0 < total; g0 += C::RES) {
+            const int n_g = (total - g0) < C::RES ? (total - g0) : C::RES;
+            if (lane == 0) s_q[warp] = 0;
+            __syncwarp();
+            // ---- dynamic pool: a lane takes the next candidate as soon as its search is over; every iteration all busy
+            // lanes execute one search_step() together
+            NoSink ns;
+            Enumerator<G, TPB, KW, NoSink> e(b, tb, kk, ns);
+            bool busy = false;
+            int myj = 0;
+            for (;;) {
+                if (!busy) {
+                    const int j = atomicAdd(&s_q[warp], 1);
+                    if (j < n_g) {
+                        const int g = g0 + j;
+                        int o = 0;   // owner = first lane whose inclusive count exceeds g
 #pragma unroll
-            for (int step = 16; step >= 1; step >>= 1) {
-                const int t = o + step;
-                const int v = __shfl_sync(0xFFFFFFFFu, incl, (t - 1) & 31);
-                if (t <= 31 && v <= g) o = t;
-            }
-            const int o_excl = __shfl_sync(0xFFFFFFFFu, excl, o);
-            const int o_kind = __shfl_sync(0xFFFFFFFFu, kind, o);
-            bool ok = false;
-            Seq<KW> seq;
-            seq.clear();
-            if (g < total) {
-                const int otid = warp * 32 + o;
-                const uint32_t cd = s_cand[(g - o_excl) * TPB + otid];
-                Board<G, TPB> ob;
-                ob.cols = s_cols + otid;
-                ob.stream = nullptr;
-                NoSink ns;
-                Enumerator<G, TPB, KW, NoSink> e(ob, tb, o_kind, ns);
-                e.pcn4 = s_pc4[2 * otid]; e.pcc4 = s_pc4[2 * otid + 1];
-                e.x = (int)(cd >> 10) - 1; e.y = (int)(cd & 63u); e.rot = (int)((cd >> 6) & 3u);
-                if (e.reachable()) {
-                    ok = true;
-                    if (e.build_finesse(seq)) seq.w[KW - 1] |= 0u;   // (overflow is reported by the owner below)
+                        for (int step = 16; step >= 1; step >>= 1) {
+                            const int t = o + step;
+                            if (t <= 31 && s_incl[warp * 32 + t - 1] <= g) o = t;
+                        }
+                        const int o_excl = o ? s_incl[warp * 32 + o - 1] : 0;
+                        const int otid = warp * 32 + o;
+                        const uint32_t cd = s_cand[(g - o_excl) * TPB + otid];
+                        Board<G, TPB> ob;
+                        ob.cols = s_cols + otid;
+                        ob.stream = nullptr;
+                        const uint64_t o_pcn4 = s_pc4[2 * otid], o_pcc4 = s_pc4[2 * otid + 1];
+                        const int okind = s_kind[otid];
+                        e.rebind(ob, okind, spawn_rot_of(tb, okind), o_pcn4, o_pcc4);
+                        e.search_begin((int)(cd >> 10) - 1, (int)(cd & 63u), (int)((cd >> 6) & 3u));
+                        busy = true;
+                        myj = j;
+                    }
+                }
+                if (__all_sync(0xFFFFFFFFu, !busy)) break;
+                if (busy && e.search_step()) {
+                    uint32_t* res = s_res + (warp * C::RES + myj) * KW;
+                    Seq<KW> seq;
+                    seq.clear();
+                    if (e.found) e.build_finesse(seq);
+#pragma unroll
+                    for (int j2 = 0; j2 < KW; j2++) res[j2] = seq.w[j2];
+                    busy = false;
                 }
             }
-#pragma unroll
-            for (int j = 0; j < KW; j++) res[j] = ok ? seq.w[j] : 0u;
             __syncwarp();
-            // ---- collect: I am the owner of round entries [a, bnd)
+            // ---- collect: I am the owner of group entries [a, bnd)
             int a = excl - g0, bnd = incl - g0;
-            a = a < 0 ? 0 : a; bnd = bnd > 32 ? 32 : bnd;
+            a = a < 0 ? 0 : a; bnd = bnd > n_g ? n_g : bnd;
             for (int t = a; t < bnd; t++) {
-                const uint32_t* rr = s_res + (warp * 32 + t) * KW;
+                const uint32_t* rr = s_res + (warp * C::RES + t) * KW;
                 if (rr[0] == 0u) continue;
                 const int c = (int)(s_cand[(g0 + t - excl) * TPB + tid] >> 8);
                 bool dup = false;
@@ -712,6 +764,15 @@ __global__ void __launch_bounds__(SCAN_TPB) scan_sums(int32_t* sums, int tiles) 
     for (int j = 0; j < SCAN_ITEMS; j++) { if (base + j < tiles) sums[base + j] = ex; ex += v[j]; }
 }
 // phase 3: offsets
+// row -> board map for expand: one thread per board writes its K consecutive rows
+__global__ void __launch_bounds__(256) fill_row_board(const int32_t* offsets, int n, int32_t* row_board, int capacity) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int a = offsets[i];
+    int b = offsets[i + 1];
+    if (b > capacity) b = capacity;
+    for (int r = a; r < b; r++) row_board[r] = i;
+}
 __global__ void __launch_bounds__(SCAN_TPB) scan_finish(const int32_t* K, int n, const int32_t* sums, int32_t* offsets) {
     __shared__ int s_warp[32];
     const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
