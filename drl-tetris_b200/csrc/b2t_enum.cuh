@@ -67,32 +67,58 @@ template <int KW> B2T_HD bool seq_equal(const Seq<KW>& a, const uint32_t* b) {
     return eq;
 }
 
-// Sink concept:  void top(const Seq<KW>&);  void finesse(const Seq<KW>&);   (overflowing sequences set .bad)
-template <class G, int S, int KW, class Sink> struct Enumerator {
+// Token writers: put(key) appends one 4-bit key token.
+template <int KW> struct SeqWriter {      // into a register Seq (host paths)
+    Seq<KW>& s;
+    bool bad;
+    B2T_HD explicit SeqWriter(Seq<KW>& s_) : s(s_), bad(false) { s.clear(); }
+    B2T_HD void put(uint32_t tok) { if (s.n < KW * 8) s.push(tok); else bad = true; }
+};
+template <int KW> struct WordWriter {     // into KW words in (shared) memory: dynamic word index costs nothing there
+    uint32_t* w;
+    uint32_t acc;
+    int n;
+    bool bad;
+    B2T_HD explicit WordWriter(uint32_t* w_) : w(w_), acc(0u), n(0), bad(false) {}
+    B2T_HD void put(uint32_t tok) {
+        if (n >= KW * 8) { bad = true; return; }
+        acc |= tok << (4 * (n & 7));
+        n++;
+        if ((n & 7) == 0) { w[(n >> 3) - 1] = acc; acc = 0u; }
+    }
+    B2T_HD void finish() {   // flush the partial word and zero the rest
+        int j = n >> 3;
+        if (n & 7) w[j++] = acc;
+        for (; j < KW; j++) w[j] = 0u;
+    }
+};
+
+// Sink concept:  void top(const Seq<KW>&, bool bad);  void finesse(const Seq<KW>&, bool bad);
+// PST = stride of the per-thread path buffer (1 on the host, block size in shared memory)
+template <class G> struct EnumGeo { static constexpr int PCAP = 2 * G::W + 6; };   // path entries: turn + rise + (lateral + rise) per column
+
+template <class G, int S, int KW, class Sink, int PST = 1> struct Enumerator {
     typedef typename G::col_t col_t;
     Board<G, S> b;      // by value (two pointers): the kernel re-points it at the owner of each pooled candidate
     Sink& sink;
     int kind, spawn_rot;
     uint64_t pcn4, pcc4;   // the four rotations of this piece, 16 bits each
     int x, y, rot;         // the probe piece of TestField
-    // test_path: the FORWARD keys of the path searched so far, newest move first (= reversed path, :152-158)
-    Seq<KW> path;
-    int path_entries;      // test_path.size() of the reference (an "n rows up" entry counts once)
+    // test_path (TestField.h:36), one byte per entry like the reference, as FORWARD keys: 3 / 1 = the lateral move undone by
+    // a left / right search step (255 / 254, :6-12), 6 = 253, 8/10/9 = 241/242/243, 16+n = "n rows up" (n times key 5)
+    uint8_t* pbuf;
+    int path_n;
     bool path_bad;
-    // finesseMove (:166-172)
-    Seq<KW> best;
-    int best_x, best_rot;
-    bool best_bad;
+    int best_x, best_rot;  // finesseMove (:166-172); its path is the test_path at the moment of success (the search stops there)
 
-    B2T_HD Enumerator(const Board<G, S>& b_, const Tabs& tb, int kind_, Sink& sink_) : b(b_), sink(sink_), kind(kind_) {
+    B2T_HD Enumerator(const Board<G, S>& b_, const Tabs& tb, int kind_, Sink& sink_, uint8_t* pbuf_) : b(b_), sink(sink_), kind(kind_), pbuf(pbuf_) {
         spawn_rot = spawn_rot_of(tb, kind);
         pcn4 = pcc4 = 0;
         for (int r = 0; r < 4; r++) {
             pcn4 |= (uint64_t)tb.pcn[kind * 4 + r] << (16 * r);
             pcc4 |= (uint64_t)tb.pcc[kind * 4 + r] << (16 * r);
         }
-        path.clear(); best.clear();
-        path_entries = 0; path_bad = best_bad = false;
+        path_n = 0; path_bad = false;
         best_x = best_rot = 0; x = y = rot = 0;
     }
     // light re-targeting for pooled searches: another board / piece, tables already packed by the owner
@@ -105,20 +131,20 @@ template <class G, int S, int KW, class Sink> struct Enumerator {
     B2T_HD bool fit() const { return fit_at(x, y, rot); }
 
     // ---- test_path bookkeeping
-    B2T_HD void path_clear() { path.clear(); path_entries = 0; path_bad = false; }
-    B2T_HD void path_key(uint32_t key) {
-        if (path.n >= KW * 8) { path_bad = true; return; }
-        path.push_front(key);
+    B2T_HD int path_entries() const { return path_n; }
+    B2T_HD void path_clear() { path_n = 0; path_bad = false; }
+    B2T_HD void path_entry(uint32_t e) {
+        if (path_n >= EnumGeo<G>::PCAP) { path_bad = true; return; }
+        pbuf[path_n * PST] = (uint8_t)e;
+        path_n++;
     }
-    B2T_HD void path_lateral(bool searching_left) { path_key(searching_left ? 3u : 1u); path_entries++; }  // 255->3, 254->1 (:6-12)
-    B2T_HD void path_turn(int turn) { path_key(turn == 1 ? 8u : turn == 2 ? 10u : 9u); path_entries++; }     // 241/242/243 (:22-32)
-    B2T_HD void path_up(int up) {  // 253 -> key 6, n -> n times key 5 (:14-20, :153-156)
+    B2T_HD void path_lateral(bool searching_left) { path_entry(searching_left ? 3u : 1u); }
+    B2T_HD void path_turn(int turn) { path_entry(turn == 1 ? 8u : turn == 2 ? 10u : 9u); }
+    B2T_HD void path_up(int up) {
         if (!up) return;
-        if (up == 253) path_key(6u);
-        else for (int i = 0; i < up; i++) path_key(5u);
-        path_entries++;
+        path_entry(up == 253 ? 6u : 16u + (uint32_t)up);
     }
-    B2T_HD bool record() { best = path; best_bad = path_bad; best_x = x; best_rot = rot; return true; }  // setFinesseMove
+    B2T_HD bool record() { best_x = x; best_rot = rot; return true; }  // setFinesseMove
 
     // moveUp (:392-410): rise while the piece fits; 253 if it rose and was resting on something, else rows risen
     B2T_HD int move_up() {
@@ -245,7 +271,7 @@ template <class G, int S, int KW, class Sink> struct Enumerator {
             dir = -1; on_fail = ST_WK_RR;
         } else if (st == ST_WK_RR) {        // doWallKick :346-352
             x = px; y = py; rot = pr;
-            if (path_entries > 1) { path_clear(); path_turn(turn); }
+            if (path_entries() > 1) { path_clear(); path_turn(turn); }
             dir = 1; on_fail = ST_WK_FAIL;
         } else if (st == ST_FINAL_L) {      // finesseIsPossible :195-196
             x = sx; y = sy; rot = sr;
@@ -281,12 +307,6 @@ template <class G, int S, int KW, class Sink> struct Enumerator {
     }
 
     // ---- emission (:37-49, :113-164)
-    B2T_HD void emit_prefix(Seq<KW>& s, int r, int xx) const {
-        const int d = (r - spawn_rot) & 3;
-        if (d) s.push(d == 1 ? 8u : d == 2 ? 10u : 9u);
-        const int n = xx - G::SPAWN_X;
-        for (int i = 0; i < (n > 0 ? n : -n); i++) s.push(n > 0 ? 3u : 1u);
-    }
     B2T_HD void emit_top(int r, int xx) {
         Seq<KW> s; s.clear();
         const int dx = xx - G::SPAWN_X;
@@ -295,20 +315,25 @@ template <class G, int S, int KW, class Sink> struct Enumerator {
         s.n = (dx < 0 ? -dx : dx) + 1 + (((r - spawn_rot) & 3) ? 1 : 0);
         sink.top(s, false);
     }
-    // forward key sequence of the recorded finesse move (useFinesseMove, :127-164); returns true if it did not fit
-    B2T_HD bool build_finesse(Seq<KW>& s) const {
-        s.clear();
-        emit_prefix(s, best_rot, best_x);
-        Seq<KW> p = best;
-        const bool bad = best_bad || (s.n + p.n + 1 > KW * 8);
-        while (p.n > 0 && s.n < KW * 8 - 1) s.push(p.pop_front());
-        s.push(7u);
-        return bad;
+    // forward key string of the recorded finesse move (useFinesseMove, :127-164): rotation, laterals to the column the
+    // search ended in, the path walked backwards (:152-158), hard drop
+    template <class Wr> B2T_HD void write_finesse(Wr& w) const {
+        const int d = (best_rot - spawn_rot) & 3;
+        if (d) w.put(d == 1 ? 8u : d == 2 ? 10u : 9u);
+        const int n = best_x - G::SPAWN_X;
+        for (int i = 0; i < (n > 0 ? n : -n); i++) w.put(n > 0 ? 3u : 1u);
+        for (int i = path_n - 1; i >= 0; i--) {
+            const uint32_t e = pbuf[i * PST];
+            if (e >= 16u) for (uint32_t k = 16u; k < e; k++) w.put(5u);
+            else w.put(e);
+        }
+        w.put(7u);
     }
     B2T_HD void emit_finesse() {
         Seq<KW> s;
-        const bool bad = build_finesse(s);
-        sink.finesse(s, bad);
+        SeqWriter<KW> w(s);
+        write_finesse(w);
+        sink.finesse(s, w.bad || path_bad);
     }
 
     // getMask (:64-111) + findNextMove (:113-125) + tryAllFinesseMoves (:174-187)

@@ -454,26 +454,39 @@ struct EParams {
 
 // Placement enumeration, one board per thread, in three phases so that the rare, expensive under-overhang search never
 // runs with one lane active while 31 wait:
-//   1. (converged) every lane scans a chunk of (column, rotation) combos of ITS board: one collision mask per combo gives
-//      the top drop (a bit in `topmask`) and the resting heights of the cavities below it (candidates, in shared memory);
-//   2. (pooled) the warp's candidates are dealt out evenly to the 32 lanes, each runs the backward search on the OWNER's
-//      board (boards are in shared memory), results return through a per-warp buffer, and each owner accepts its results
-//      in candidate order (first-occurrence de-duplication, action_list.py:14) straight into their final list slots:
+//   1. (converged) every lane scans (column, rotation) combos of ITS board: one collision mask per combo gives the top
+//      drop (a bit in `topmask`) and the resting heights of the cavities below it (candidates, in shared memory); the scan
+//      pauses (warp-uniformly) only if some lane's candidate slots could overflow;
+//   2. (pooled) the warp's candidates form a work queue; a lane takes the next candidate as soon as its search ends and all
+//      busy lanes execute Enumerator::search_step() together on the OWNERS' boards (shared memory); results return through
+//      a per-warp buffer and each owner accepts its results in candidate order (first-occurrence de-duplication,
+//      action_list.py:14) straight into their final list slots:
 //      slot = #top drops with combo <= c  +  #finesse entries accepted before;
 //   3. every lane writes its top drops into the remaining slots.
 // Emission order is exactly TestField::getMask's: combos ascending (x-major, rotation-minor), top drop first, then the
 // combo's cavities by increasing height.
+constexpr int ETPB = 64;              // threads per block of the enumerate kernel (small: 65 536 boards must still fill 148 SMs)
+constexpr int EWARPS = ETPB / 32;
+
 template <class G> struct EnumCfg {
-    static constexpr int CCAP = 64;                                  // candidate slots per thread per chunk
+    static constexpr int CCAP = 64;                                  // candidate slots per thread between two pooled searches
     static constexpr int PER_COMBO = (G::H - 1) / 2;                 // resting heights differ by >= 2 and start at 2
-    static constexpr int CH = (CCAP / PER_COMBO) < 1 ? 1 : (CCAP / PER_COMBO);   // combos per chunk (never overflows CCAP)
     static constexpr int NCOMBO = 4 * G::W;
-    static constexpr int NCHUNK = (NCOMBO + CH - 1) / CH;
     static constexpr int ACAP = G::KMAX;                             // accepted finesse entries per board (cannot overflow before the list does)
+    static constexpr int RES = 128;                                  // pooled results buffered per warp between acceptances
+    static constexpr int PCAP = EnumGeo<G>::PCAP;
     static_assert(NCOMBO <= 128, "topmask is 128 bits");
-    static constexpr int RES = 64;                                   // pooled results buffered per warp between acceptances
-    static constexpr int SMEM = G::NCOL * TPB * (int)sizeof(typename G::col_t) + CCAP * TPB * 2 + ACAP * TPB + TPB * 16 +
-                                WARPS * RES * G::KEYW * 4 + WARPS * 32 * 4 + WARPS * 4 + TPB * 4 + 128;
+    static_assert(PER_COMBO <= CCAP, "a single combo must fit the candidate slots");
+    static constexpr int O_CAND = G::NCOL * ETPB * (int)sizeof(typename G::col_t);
+    static constexpr int O_PC4 = O_CAND + CCAP * ETPB * 2;
+    static constexpr int O_RES = O_PC4 + ETPB * 16;
+    static constexpr int O_INCL = O_RES + EWARPS * RES * G::KEYW * 4;
+    static constexpr int O_Q = O_INCL + EWARPS * 32 * 4;
+    static constexpr int O_KIND = O_Q + EWARPS * 4 + ((EWARPS & 1) ? 4 : 0);
+    static constexpr int O_TAB = O_KIND + ETPB * 4;
+    static constexpr int O_ACC = O_TAB + 128;
+    static constexpr int O_PBUF = O_ACC + ACAP * ETPB;
+    static constexpr int SMEM = O_PBUF + PCAP * ETPB + 16;
 };
 
 struct NoSink {
@@ -489,31 +502,32 @@ __device__ __forceinline__ int rank128(uint64_t lo, uint64_t hi, int nbits) {  /
 }
 
 template <class G>
-__global__ void __launch_bounds__(TPB) enumerate_kernel(const EParams p) {
+__global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
     typedef typename G::col_t col_t;
     typedef EnumCfg<G> C;
     constexpr int KW = G::KEYW;
     extern __shared__ __align__(16) unsigned char smem[];
     col_t* s_cols = reinterpret_cast<col_t*>(smem);
-    uint16_t* s_cand = reinterpret_cast<uint16_t*>(smem + G::NCOL * TPB * sizeof(col_t));        // [CCAP][TPB]
-    uint8_t* s_acc = reinterpret_cast<uint8_t*>(s_cand + C::CCAP * TPB);                           // [ACAP][TPB] combo of accepted entry
-    uint64_t* s_pc4 = reinterpret_cast<uint64_t*>(s_acc + C::ACAP * TPB);                          // [TPB][2] pcn4, pcc4 of the owner's piece
-    uint32_t* s_res = reinterpret_cast<uint32_t*>(s_pc4 + 2 * TPB);                                // [WARPS][RES][KW]
-    int* s_incl = reinterpret_cast<int*>(s_res + WARPS * C::RES * KW);                             // [WARPS][32] inclusive candidate counts
-    int* s_q = s_incl + WARPS * 32;                                                                // [WARPS] work-queue heads
-    int* s_kind = s_q + WARPS;                                                                     // [TPB] piece of every thread's board
-    uint16_t* s_tab = reinterpret_cast<uint16_t*>(s_kind + TPB);
+    uint16_t* s_cand = reinterpret_cast<uint16_t*>(smem + C::O_CAND);   // [CCAP][ETPB]
+    uint64_t* s_pc4 = reinterpret_cast<uint64_t*>(smem + C::O_PC4);     // [ETPB][2] pcn4, pcc4 of the owner's piece
+    uint32_t* s_res = reinterpret_cast<uint32_t*>(smem + C::O_RES);     // [EWARPS][RES][KW]
+    int* s_incl = reinterpret_cast<int*>(smem + C::O_INCL);             // [EWARPS][32] inclusive candidate counts
+    int* s_q = reinterpret_cast<int*>(smem + C::O_Q);                   // [EWARPS] work-queue heads
+    int* s_kind = reinterpret_cast<int*>(smem + C::O_KIND);             // [ETPB]
+    uint16_t* s_tab = reinterpret_cast<uint16_t*>(smem + C::O_TAB);
+    uint8_t* s_acc = smem + C::O_ACC;                                   // [ACAP][ETPB] combo of every accepted finesse entry
+    uint8_t* s_pbuf = smem + C::O_PBUF;                                 // [PCAP][ETPB] this lane's search path
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int i = blockIdx.x * TPB + tid;
+    const int i = blockIdx.x * ETPB + tid;
     if (tid < 28) { s_tab[tid] = p.tabs.pcn[tid]; s_tab[32 + tid] = p.tabs.pcc[tid]; }
     Tabs tb;
     tb.pcn = s_tab; tb.pcc = s_tab + 32;
     tb.piece = p.tabs.piece; tb.hole = p.tabs.hole; tb.powtab = p.tabs.powtab;
     tb.piece_len = p.tabs.piece_len; tb.hole_len = p.tabs.hole_len; tb.spawn_rots = p.tabs.spawn_rots;
-    Board<G, TPB> b;
+    Board<G, ETPB> b;
     b.cols = s_cols + tid;
     b.stream = nullptr;
-    board_init_walls<G, TPB>(b);
+    board_init_walls<G, ETPB>(b);
     __syncthreads();
     const bool active = i < p.n;
     int gi = 0, kind = 7, cur_rot = 0;
@@ -545,17 +559,20 @@ __global__ void __launch_bounds__(TPB) enumerate_kernel(const EParams p) {
     uint32_t* lst = p.plc + (size_t)gi * G::KMAX * KW;      // this board's list (only dereferenced by active lanes)
     uint64_t top_lo = 0, top_hi = 0;
     int nacc = 0, bad = 0;
+    NoSink ns;
+    Enumerator<G, ETPB, KW, NoSink, ETPB> e(b, tb, kk, ns, s_pbuf + tid);
     __syncwarp();
 
-    for (int chunk = 0; chunk < C::NCHUNK; chunk++) {
-        // ---- phase 1: my combos of this chunk
-        int ncand = 0;
-        for (int cc = 0; cc < C::CH; cc++) {
-            const int c = chunk * C::CH + cc;
+    int c_next = 0;
+    while (c_next < C::NCOMBO) {
+        // ---- phase 1: my combos, until some lane could run out of candidate slots
+        int ncand = 0, c = c_next;
+        for (; c < C::NCOMBO; c++) {
+            if (__any_sync(0xFFFFFFFFu, ncand > C::CCAP - C::PER_COMBO)) break;
             const int r0 = c & 3, xx = (c >> 2) - 1;
-            if (c < C::NCOMBO && r0 < nrot) {
+            if (r0 < nrot) {
                 const int r = (kind == 6) ? cur_rot : r0;
-                const col_t cm = collide_mask<G, TPB>(b, xx, (uint32_t)(pcc4 >> (16 * r)) & 0xFFFFu);
+                const col_t cm = collide_mask<G, ETPB>(b, xx, (uint32_t)(pcc4 >> (16 * r)) & 0xFFFFu);
                 if (!((cm >> G::YB) & 1)) {
                     if (c < 64) top_lo |= 1ull << c; else top_hi |= 1ull << (c - 64);
                     int yy = rest_from<G>(cm, 0) + 2;
@@ -564,7 +581,7 @@ __global__ void __launch_bounds__(TPB) enumerate_kernel(const EParams p) {
                         free_ &= (col_t)((G::one() << (G::H - 1 - yy)) - 1);
                         if (!free_) break;
                         const int rest = rest_from<G>(cm, yy + ctz(free_));
-                        if (ncand < C::CCAP) s_cand[ncand * TPB + tid] = (uint16_t)((c << 8) | (r << 6) | rest);
+                        if (ncand < C::CCAP) s_cand[ncand * ETPB + tid] = (uint16_t)((c << 8) | (r << 6) | rest);
                         else bad = 1;
                         ncand++;
                         yy = rest + 1;
@@ -572,6 +589,7 @@ __global__ void __launch_bounds__(TPB) enumerate_kernel(const EParams p) {
                 }
             }
         }
+        c_next = c;
         if (ncand > C::CCAP) ncand = C::CCAP;
         // ---- phase 2: pool the warp's candidates
         int incl = ncand;
@@ -588,10 +606,6 @@ __global__ void __launch_bounds__(TPB) enumerate_kernel(const EParams p) {
             const int n_g = (total - g0) < C::RES ? (total - g0) : C::RES;
             if (lane == 0) s_q[warp] = 0;
             __syncwarp();
-            // ---- dynamic pool: a lane takes the next candidate as soon as its search is over; every iteration all busy
-            // lanes execute one search_step() together
-            NoSink ns;
-            Enumerator<G, TPB, KW, NoSink> e(b, tb, kk, ns);
             bool busy = false;
             int myj = 0;
             for (;;) {
@@ -607,13 +621,12 @@ __global__ void __launch_bounds__(TPB) enumerate_kernel(const EParams p) {
                         }
                         const int o_excl = o ? s_incl[warp * 32 + o - 1] : 0;
                         const int otid = warp * 32 + o;
-                        const uint32_t cd = s_cand[(g - o_excl) * TPB + otid];
-                        Board<G, TPB> ob;
+                        const uint32_t cd = s_cand[(g - o_excl) * ETPB + otid];
+                        Board<G, ETPB> ob;
                         ob.cols = s_cols + otid;
                         ob.stream = nullptr;
-                        const uint64_t o_pcn4 = s_pc4[2 * otid], o_pcc4 = s_pc4[2 * otid + 1];
                         const int okind = s_kind[otid];
-                        e.rebind(ob, okind, spawn_rot_of(tb, okind), o_pcn4, o_pcc4);
+                        e.rebind(ob, okind, spawn_rot_of(tb, okind), s_pc4[2 * otid], s_pc4[2 * otid + 1]);
                         e.search_begin((int)(cd >> 10) - 1, (int)(cd & 63u), (int)((cd >> 6) & 3u));
                         busy = true;
                         myj = j;
@@ -622,11 +635,11 @@ __global__ void __launch_bounds__(TPB) enumerate_kernel(const EParams p) {
                 if (__all_sync(0xFFFFFFFFu, !busy)) break;
                 if (busy && e.search_step()) {
                     uint32_t* res = s_res + (warp * C::RES + myj) * KW;
-                    Seq<KW> seq;
-                    seq.clear();
-                    if (e.found) e.build_finesse(seq);
-#pragma unroll
-                    for (int j2 = 0; j2 < KW; j2++) res[j2] = seq.w[j2];
+                    if (e.found) {
+                        WordWriter<KW> w(res);
+                        e.write_finesse(w);
+                        w.finish();
+                    } else res[0] = 0u;
                     busy = false;
                 }
             }
@@ -637,10 +650,10 @@ __global__ void __launch_bounds__(TPB) enumerate_kernel(const EParams p) {
             for (int t = a; t < bnd; t++) {
                 const uint32_t* rr = s_res + (warp * C::RES + t) * KW;
                 if (rr[0] == 0u) continue;
-                const int c = (int)(s_cand[(g0 + t - excl) * TPB + tid] >> 8);
+                const int cc = (int)(s_cand[(g0 + t - excl) * ETPB + tid] >> 8);
                 bool dup = false;
                 for (int f = 0; f < nacc && !dup; f++) {
-                    const int fc = s_acc[f * TPB + tid];
+                    const int fc = s_acc[f * ETPB + tid];
                     const int slot = off + rank128(top_lo, top_hi, fc + 1) + f;
                     if (slot < G::KMAX) {
                         const uint32_t* q = lst + (size_t)slot * KW;
@@ -651,12 +664,12 @@ __global__ void __launch_bounds__(TPB) enumerate_kernel(const EParams p) {
                     }
                 }
                 if (dup) continue;
-                const int slot = off + rank128(top_lo, top_hi, c + 1) + nacc;
+                const int slot = off + rank128(top_lo, top_hi, cc + 1) + nacc;
                 if (slot < G::KMAX && nacc < C::ACAP) {
                     uint4* dst = reinterpret_cast<uint4*>(lst + (size_t)slot * KW);
 #pragma unroll
                     for (int j = 0; j < KW / 4; j++) dst[j] = make_uint4(rr[4 * j], rr[4 * j + 1], rr[4 * j + 2], rr[4 * j + 3]);
-                    s_acc[nacc * TPB + tid] = (uint8_t)c;
+                    s_acc[nacc * ETPB + tid] = (uint8_t)cc;
                 } else bad = 1;
                 nacc++;
             }
@@ -670,7 +683,7 @@ __global__ void __launch_bounds__(TPB) enumerate_kernel(const EParams p) {
         for (int c = 0; c < C::NCOMBO; c++) {
             const bool has = (c < 64) ? ((top_lo >> c) & 1ull) : ((top_hi >> (c - 64)) & 1ull);
             if (!has) continue;
-            while (f < nacc && s_acc[f * TPB + tid] < c) f++;
+            while (f < nacc && s_acc[f * ETPB + tid] < c) f++;
             const int slot = off + ntop + f;
             const int r = (kind == 6) ? cur_rot : (c & 3);
             const uint64_t t = top_drop_tokens((r - spawn) & 3, ((c >> 2) - 1) - G::SPAWN_X);
@@ -862,7 +875,7 @@ template <class G> struct Launch {
     }
     static cudaError_t enumerate(const EParams& p, cudaStream_t s) {
         if (p.n <= 0) return cudaSuccess;
-        enumerate_kernel<G><<<(p.n + TPB - 1) / TPB, TPB, EnumCfg<G>::SMEM, s>>>(p);
+        enumerate_kernel<G><<<(p.n + ETPB - 1) / ETPB, ETPB, EnumCfg<G>::SMEM, s>>>(p);
         return cudaGetLastError();
     }
     static cudaError_t unpack(const uint32_t* plc, const int32_t* kc, const int32_t* idx, int n, int kmax, int lmax, uint8_t* keys,

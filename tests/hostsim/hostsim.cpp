@@ -176,7 +176,8 @@ template <int H, int W> struct HS : HSBase {
         sink.init(lst + off * KW, cap - off);
         const PS& me = g.p[player];
         if (me.kind <= 6) {
-            Enumerator<G, 1, KW, ListSink<KW>> e(g.b[player], tb, me.kind, sink);
+            uint8_t pbuf[EnumGeo<G>::PCAP];
+            Enumerator<G, 1, KW, ListSink<KW>> e(g.b[player], tb, me.kind, sink, pbuf);
             e.run(me.rot);
         }
         *bad = sink.bad;
