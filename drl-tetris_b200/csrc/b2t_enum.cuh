@@ -74,7 +74,7 @@ template <int KW> struct SeqWriter {      // into a register Seq (host paths)
     B2T_HD explicit SeqWriter(Seq<KW>& s_) : s(s_), bad(false) { s.clear(); }
     B2T_HD void put(uint32_t tok) { if (s.n < KW * 8) s.push(tok); else bad = true; }
 };
-template <int KW> struct WordWriter {     // into KW words in (shared) memory: dynamic word index costs nothing there
+template <int KW, int WS = 1> struct WordWriter {     // into KW words (stride WS) in (shared) memory: dynamic word index costs nothing there
     uint32_t* w;
     uint32_t acc;
     int n;
@@ -84,12 +84,12 @@ template <int KW> struct WordWriter {     // into KW words in (shared) memory: d
         if (n >= KW * 8) { bad = true; return; }
         acc |= tok << (4 * (n & 7));
         n++;
-        if ((n & 7) == 0) { w[(n >> 3) - 1] = acc; acc = 0u; }
+        if ((n & 7) == 0) { w[((n >> 3) - 1) * WS] = acc; acc = 0u; }
     }
     B2T_HD void finish() {   // flush the partial word and zero the rest
         int j = n >> 3;
-        if (n & 7) w[j++] = acc;
-        for (; j < KW; j++) w[j] = 0u;
+        if (n & 7) w[(j++) * WS] = acc;
+        for (; j < KW; j++) w[j * WS] = 0u;
     }
 };
 
@@ -213,6 +213,7 @@ template <class G, int S, int KW, class Sink, int PST = 1> struct Enumerator {
     }
     // one iteration; true when the search is over (result in `found`; on success path/x/rot hold the recorded move)
     B2T_HD bool search_step() {
+        B2T_COUNT(5);
         // ---- cheap stage transitions
         if (st == ST_SIDE) {                                   // reverseWallkick :262-266
             const bool fr = fit_at(sx + 1, sy, sr), fl = fit_at(sx - 1, sy, sr);
@@ -280,8 +281,10 @@ template <class G, int S, int KW, class Sink, int PST = 1> struct Enumerator {
             dir = 1; clear = true; on_fail = ST_DONE;
         }
         if (dir != 0) {
+            B2T_COUNT(6);
             bool success = false;
             for (;;) {
+                B2T_COUNT(7);
                 if (!rise_first) {
                     if (!fit_at(x + dir, y, rot)) break;
                     x += dir;
@@ -318,12 +321,16 @@ template <class G, int S, int KW, class Sink, int PST = 1> struct Enumerator {
     // forward key string of the recorded finesse move (useFinesseMove, :127-164): rotation, laterals to the column the
     // search ended in, the path walked backwards (:152-158), hard drop
     template <class Wr> B2T_HD void write_finesse(Wr& w) const {
-        const int d = (best_rot - spawn_rot) & 3;
+        write_finesse_raw<Wr, PST>(w, pbuf, path_n, best_x, best_rot, spawn_rot);
+    }
+    template <class Wr, int PS2>
+    B2T_HD static void write_finesse_raw(Wr& w, const uint8_t* pb, int pn, int bx_, int brot, int spawn) {
+        const int d = (brot - spawn) & 3;
         if (d) w.put(d == 1 ? 8u : d == 2 ? 10u : 9u);
-        const int n = best_x - G::SPAWN_X;
+        const int n = bx_ - G::SPAWN_X;
         for (int i = 0; i < (n > 0 ? n : -n); i++) w.put(n > 0 ? 3u : 1u);
-        for (int i = path_n - 1; i >= 0; i--) {
-            const uint32_t e = pbuf[i * PST];
+        for (int i = pn - 1; i >= 0; i--) {
+            const uint32_t e = pb[i * PS2];
             if (e >= 16u) for (uint32_t k = 16u; k < e; k++) w.put(5u);
             else w.put(e);
         }

@@ -473,20 +473,21 @@ template <class G> struct EnumCfg {
     static constexpr int PER_COMBO = (G::H - 1) / 2;                 // resting heights differ by >= 2 and start at 2
     static constexpr int NCOMBO = 4 * G::W;
     static constexpr int ACAP = G::KMAX;                             // accepted finesse entries per board (cannot overflow before the list does)
-    static constexpr int RES = 128;                                  // pooled results buffered per warp between acceptances
+    static constexpr int RES = 128;                                  // pooled results buffered per warp between acceptances (smem: 7 blocks/SM)
     static constexpr int PCAP = EnumGeo<G>::PCAP;
+    static constexpr int RSW = 1 + (PCAP + 3) / 4;                   // result slot: header word + the raw search path
     static_assert(NCOMBO <= 128, "topmask is 128 bits");
     static_assert(PER_COMBO <= CCAP, "a single combo must fit the candidate slots");
     static constexpr int O_CAND = G::NCOL * ETPB * (int)sizeof(typename G::col_t);
     static constexpr int O_PC4 = O_CAND + CCAP * ETPB * 2;
     static constexpr int O_RES = O_PC4 + ETPB * 16;
-    static constexpr int O_INCL = O_RES + EWARPS * RES * G::KEYW * 4;
+    static constexpr int O_INCL = O_RES + EWARPS * RES * RSW * 4;
     static constexpr int O_Q = O_INCL + EWARPS * 32 * 4;
     static constexpr int O_KIND = O_Q + EWARPS * 4 + ((EWARPS & 1) ? 4 : 0);
     static constexpr int O_TAB = O_KIND + ETPB * 4;
     static constexpr int O_ACC = O_TAB + 128;
     static constexpr int O_PBUF = O_ACC + ACAP * ETPB;
-    static constexpr int SMEM = O_PBUF + PCAP * ETPB + 16;
+    static constexpr int SMEM = O_PBUF + G::KEYW * ETPB * 4 + 16;   // O_PBUF: per-thread scratch for the sequence being accepted
 };
 
 struct NoSink {
@@ -510,13 +511,13 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
     col_t* s_cols = reinterpret_cast<col_t*>(smem);
     uint16_t* s_cand = reinterpret_cast<uint16_t*>(smem + C::O_CAND);   // [CCAP][ETPB]
     uint64_t* s_pc4 = reinterpret_cast<uint64_t*>(smem + C::O_PC4);     // [ETPB][2] pcn4, pcc4 of the owner's piece
-    uint32_t* s_res = reinterpret_cast<uint32_t*>(smem + C::O_RES);     // [EWARPS][RES][KW]
+    uint32_t* s_res = reinterpret_cast<uint32_t*>(smem + C::O_RES);     // [EWARPS][RES][RSW] header + raw path of every pooled search
     int* s_incl = reinterpret_cast<int*>(smem + C::O_INCL);             // [EWARPS][32] inclusive candidate counts
     int* s_q = reinterpret_cast<int*>(smem + C::O_Q);                   // [EWARPS] work-queue heads
     int* s_kind = reinterpret_cast<int*>(smem + C::O_KIND);             // [ETPB]
     uint16_t* s_tab = reinterpret_cast<uint16_t*>(smem + C::O_TAB);
     uint8_t* s_acc = smem + C::O_ACC;                                   // [ACAP][ETPB] combo of every accepted finesse entry
-    uint8_t* s_pbuf = smem + C::O_PBUF;                                 // [PCAP][ETPB] this lane's search path
+    uint32_t* s_seq = reinterpret_cast<uint32_t*>(smem + C::O_PBUF);    // [KW][ETPB] key string being accepted by this owner
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i = blockIdx.x * ETPB + tid;
     if (tid < 28) { s_tab[tid] = p.tabs.pcn[tid]; s_tab[32 + tid] = p.tabs.pcc[tid]; }
@@ -560,7 +561,7 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
     uint64_t top_lo = 0, top_hi = 0;
     int nacc = 0, bad = 0;
     NoSink ns;
-    Enumerator<G, ETPB, KW, NoSink, ETPB> e(b, tb, kk, ns, s_pbuf + tid);
+    Enumerator<G, ETPB, KW, NoSink, 1> e(b, tb, kk, ns, nullptr);
     __syncwarp();
 
     int c_next = 0;
@@ -627,6 +628,8 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
                         ob.stream = nullptr;
                         const int okind = s_kind[otid];
                         e.rebind(ob, okind, spawn_rot_of(tb, okind), s_pc4[2 * otid], s_pc4[2 * otid + 1]);
+                        e.pbuf = reinterpret_cast<uint8_t*>(s_res + (warp * C::RES + j) * C::RSW + 1);   // the path is built in the result slot
+                        e.path_clear();
                         e.search_begin((int)(cd >> 10) - 1, (int)(cd & 63u), (int)((cd >> 6) & 3u));
                         busy = true;
                         myj = j;
@@ -634,12 +637,9 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
                 }
                 if (__all_sync(0xFFFFFFFFu, !busy)) break;
                 if (busy && e.search_step()) {
-                    uint32_t* res = s_res + (warp * C::RES + myj) * KW;
-                    if (e.found) {
-                        WordWriter<KW> w(res);
-                        e.write_finesse(w);
-                        w.finish();
-                    } else res[0] = 0u;
+                    s_res[(warp * C::RES + myj) * C::RSW] = e.found
+                        ? (0x80000000u | ((uint32_t)e.path_n << 16) | ((uint32_t)((e.best_x + 8) & 255) << 8) | ((uint32_t)e.best_rot << 2) | (e.path_bad ? 1u : 0u))
+                        : 0u;
                     busy = false;
                 }
             }
@@ -647,9 +647,21 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
             // ---- collect: I am the owner of group entries [a, bnd)
             int a = excl - g0, bnd = incl - g0;
             a = a < 0 ? 0 : a; bnd = bnd > n_g ? n_g : bnd;
-            for (int t = a; t < bnd; t++) {
-                const uint32_t* rr = s_res + (warp * C::RES + t) * KW;
-                if (rr[0] == 0u) continue;
+            // lanes first skip over their failed searches (cheap), so that the k-th SUCCESS of every owner is expanded,
+            // de-duplicated and stored in the same warp iteration
+            for (int t = a;; t++) {
+                while (t < bnd && s_res[(warp * C::RES + t) * C::RSW] == 0u) t++;
+                if (!__any_sync(0xFFFFFFFFu, t < bnd)) break;
+                if (t >= bnd) continue;
+                const uint32_t* slot_in = s_res + (warp * C::RES + t) * C::RSW;
+                const uint32_t hd = slot_in[0];
+                // expand the recorded move into its forward key string (useFinesseMove, TestField.cpp:127-164)
+                uint32_t* rr = s_seq + tid;                     // word j at rr[j * ETPB]
+                WordWriter<KW, ETPB> w(rr);
+                Enumerator<G, ETPB, KW, NoSink, 1>::template write_finesse_raw<WordWriter<KW, ETPB>, 1>(
+                    w, reinterpret_cast<const uint8_t*>(slot_in + 1), (int)((hd >> 16) & 255u), (int)((hd >> 8) & 255u) - 8, (int)((hd >> 2) & 3u), spawn);
+                w.finish();
+                if (w.bad || (hd & 1u)) bad = 1;
                 const int cc = (int)(s_cand[(g0 + t - excl) * ETPB + tid] >> 8);
                 bool dup = false;
                 for (int f = 0; f < nacc && !dup; f++) {
@@ -659,7 +671,7 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
                         const uint32_t* q = lst + (size_t)slot * KW;
                         bool eq = true;
 #pragma unroll
-                        for (int j = 0; j < KW; j++) eq = eq && (q[j] == rr[j]);
+                        for (int j = 0; j < KW; j++) eq = eq && (q[j] == rr[j * ETPB]);
                         dup = eq;
                     }
                 }
@@ -668,7 +680,8 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
                 if (slot < G::KMAX && nacc < C::ACAP) {
                     uint4* dst = reinterpret_cast<uint4*>(lst + (size_t)slot * KW);
 #pragma unroll
-                    for (int j = 0; j < KW / 4; j++) dst[j] = make_uint4(rr[4 * j], rr[4 * j + 1], rr[4 * j + 2], rr[4 * j + 3]);
+                    for (int j = 0; j < KW / 4; j++)
+                        dst[j] = make_uint4(rr[(4 * j) * ETPB], rr[(4 * j + 1) * ETPB], rr[(4 * j + 2) * ETPB], rr[(4 * j + 3) * ETPB]);
                     s_acc[nacc * ETPB + tid] = (uint8_t)cc;
                 } else bad = 1;
                 nacc++;
