@@ -385,25 +385,42 @@ struct Out {
 };
 static void* dev_out(const Arena& a, const Out& o) { return o.dst ? a.d + o.off : nullptr; }
 
+// Pinned (cudaMallocHost / cudaHostRegister'ed, e.g. torch pin_memory) caller buffers are copied straight to / from the
+// device arena; pageable ones go through the handle's pinned staging (one extra host memcpy).
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
 static int stage_in(b2t_handle* h, std::vector<In*> ins, cudaStream_t s) {
     size_t total = 0;
     for (auto i : ins) if (i->src) total += (i->bytes + 255) & ~(size_t)255;
     CK(h->in.reserve(total + 256));
-    for (auto i : ins) if (i->src) { i->off = h->in.take(i->bytes); memcpy(h->in.h + i->off, i->src, i->bytes); }
-    if (h->in.at) CK(cudaMemcpyAsync(h->in.d, h->in.h, h->in.at, cudaMemcpyHostToDevice, s));
+    for (auto i : ins) {
+        if (!i->src || !i->bytes) { if (i->src) i->off = h->in.take(1); continue; }
+        i->off = h->in.take(i->bytes);
+        const void* from = i->src;
+        if (!is_pinned(from)) { memcpy(h->in.h + i->off, i->src, i->bytes); from = h->in.h + i->off; }
+        CK(cudaMemcpyAsync(h->in.d + i->off, from, i->bytes, cudaMemcpyHostToDevice, s));
+    }
     return B2T_OK;
 }
 static int plan_out(b2t_handle* h, std::vector<Out*> outs) {
     size_t total = 0;
     for (auto o : outs) if (o->dst) total += (o->bytes + 255) & ~(size_t)255;
     CK(h->out.reserve(total + 256));
-    for (auto o : outs) if (o->dst) o->off = h->out.take(o->bytes);
+    for (auto o : outs) if (o->dst) o->off = h->out.take(o->bytes ? o->bytes : 1);
     return B2T_OK;
 }
 static int fetch_out(b2t_handle* h, std::vector<Out*> outs, cudaStream_t s) {
-    if (h->out.at) CK(cudaMemcpyAsync(h->out.h, h->out.d, h->out.at, cudaMemcpyDeviceToHost, s));
+    std::vector<Out*> staged;
+    for (auto o : outs) {
+        if (!o->dst || !o->bytes) continue;
+        if (is_pinned(o->dst)) CK(cudaMemcpyAsync(o->dst, h->out.d + o->off, o->bytes, cudaMemcpyDeviceToHost, s));
+        else { CK(cudaMemcpyAsync(h->out.h + o->off, h->out.d + o->off, o->bytes, cudaMemcpyDeviceToHost, s)); staged.push_back(o); }
+    }
     CK(cudaStreamSynchronize(s));
-    for (auto o : outs) if (o->dst) memcpy(o->dst, h->out.h + o->off, o->bytes);
+    for (auto o : staged) memcpy(o->dst, h->out.h + o->off, o->bytes);
     return B2T_OK;
 }
 
