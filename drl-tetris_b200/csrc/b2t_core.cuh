@@ -372,9 +372,11 @@ struct PS {
     uint32_t piece_ctr;
     int hole_ctr, hi12;  // hi12: p0 = seed16, p1 = game flags
     int gq_n, flags;
-    int gq_count[GQ_CAP];
-    int32_t gq_delay[GQ_CAP];
+    // GarbageHandler::garbage (Garbage.h:27): the queue is almost always empty, so it lives in (shared) memory, not in
+    // registers: 9 words, word j at gq[j*S]: 0..2 = six int16 counts, 3..8 = six int32 release times
+    uint32_t* gq;
 };
+constexpr int GQ_WORDS = 3 + GQ_CAP;   // state words 14..22 of a player
 // game flags (player 1, word 12 high half)
 constexpr int GF_ROUND_OVER = 1, GF_ENV_DONE = 2, GF_WINNER_SHIFT = 2, GF_GQ_OVERFLOW = 16, GF_RNG_OVERFLOW = 32;
 
@@ -389,11 +391,6 @@ B2T_HD void ps_unpack(PS& s, const uint32_t* w) {
     s.min_remaining = (int32_t)w[10]; s.piece_ctr = w[11];
     s.hole_ctr = w[12] & 0xFFFF; s.hi12 = w[12] >> 16;
     s.gq_n = w[13] & 255; s.flags = (w[13] >> 8) & 255;
-#pragma unroll
-    for (int i = 0; i < GQ_CAP; i++) {
-        s.gq_count[i] = (int16_t)(w[14 + (i >> 1)] >> (16 * (i & 1)));
-        s.gq_delay[i] = (int32_t)w[17 + i];
-    }
 }
 B2T_HD void ps_pack(const PS& s, uint32_t* w) {
     w[0] = (uint32_t)(s.kind & 7) | ((uint32_t)(s.rot & 3) << 3) | ((uint32_t)(s.next & 7) << 5) |
@@ -408,13 +405,7 @@ B2T_HD void ps_pack(const PS& s, uint32_t* w) {
     w[10] = (uint32_t)s.min_remaining; w[11] = s.piece_ctr;
     w[12] = (uint32_t)(s.hole_ctr & 0xFFFF) | ((uint32_t)(s.hi12 & 0xFFFF) << 16);
     w[13] = (uint32_t)(s.gq_n & 255) | ((uint32_t)(s.flags & 255) << 8);
-    w[14] = w[15] = w[16] = 0;
-#pragma unroll
-    for (int i = 0; i < GQ_CAP; i++) {
-        w[14 + (i >> 1)] |= (uint32_t)(s.gq_count[i] & 0xFFFF) << (16 * (i & 1));
-        w[17 + i] = (uint32_t)s.gq_delay[i];
-    }
-    w[23] = 0;
+    w[23] = 0;   // words 14..22 (the garbage queue) never pass through registers
 }
 
 // ---- DropDelay.cpp
@@ -432,60 +423,75 @@ B2T_HD bool dd_check(PS& s, int32_t t) {  // :3-21 (increaseDropDelay is the con
 B2T_HD void dd_reset(PS& s, int32_t t) { s.drop_delay_time = t; s.lockdown = 0; }                  // :23-26
 B2T_HD void dd_set(PS& s, int32_t t) { if (!s.lockdown) s.lockdown_time = t + 400; s.lockdown = 1; }  // :37-41
 
-// ---- Garbage.cpp (queue front is index 0)
-B2T_HD void gq_pop(PS& s) {
-#pragma unroll
-    for (int i = 0; i + 1 < GQ_CAP; i++) { s.gq_count[i] = s.gq_count[i + 1]; s.gq_delay[i] = s.gq_delay[i + 1]; }
-    s.gq_count[GQ_CAP - 1] = 0; s.gq_delay[GQ_CAP - 1] = 0;
+// ---- Garbage.cpp (queue front is index 0); S = stride of the queue words
+template <int S> B2T_HD int gq_count_at(const PS& s, int i) { return (int)(int16_t)(s.gq[(i >> 1) * S] >> (16 * (i & 1))); }
+template <int S> B2T_HD void gq_set_count(PS& s, int i, int v) {
+    uint32_t& w = s.gq[(i >> 1) * S];
+    const int sh = 16 * (i & 1);
+    w = (w & ~(0xFFFFu << sh)) | ((uint32_t)(v & 0xFFFF) << sh);
+}
+template <int S> B2T_HD int32_t gq_delay_at(const PS& s, int i) { return (int32_t)s.gq[(3 + i) * S]; }
+template <int S> B2T_HD void gq_set_delay(PS& s, int i, int32_t v) { s.gq[(3 + i) * S] = (uint32_t)v; }
+template <int S> B2T_HD void gq_pop(PS& s) {
+    const uint32_t c0 = s.gq[0], c1 = s.gq[S], c2 = s.gq[2 * S];
+    s.gq[0] = (c0 >> 16) | (c1 << 16); s.gq[S] = (c1 >> 16) | (c2 << 16); s.gq[2 * S] = c2 >> 16;
+    for (int i = 0; i + 1 < GQ_CAP; i++) s.gq[(3 + i) * S] = s.gq[(4 + i) * S];
+    s.gq[(3 + GQ_CAP - 1) * S] = 0u;
     s.gq_n--;
 }
-B2T_HD int gq_total(const PS& s) {  // :9-14
+template <int S> B2T_HD void gq_clear(PS& s) {
+    for (int j = 0; j < GQ_WORDS; j++) s.gq[j * S] = 0u;
+    s.gq_n = 0;
+}
+template <int S> B2T_HD int gq_total(const PS& s) {  // :9-14
+    if (s.gq_n == 0) return 0;
     int t = 0;
-#pragma unroll
-    for (int i = 0; i < GQ_CAP; i++) t += (i < s.gq_n) ? s.gq_count[i] : 0;
+    for (int i = 0; i < s.gq_n; i++) t += gq_count_at<S>(s, i);
     return t & 0xFFFF;
 }
-B2T_HD void gq_add(PS& s, int amount, int32_t t) {  // :22-24
-    if (s.gq_n >= GQ_CAP) { s.flags |= 1; return; }  // sticky overflow, surfaced through b2t_status
-    // select form on every slot: a conditional store would be turned into a dynamically indexed one, which drags the
-    // whole register-resident game state into local memory
-#pragma unroll
-    for (int i = 0; i < GQ_CAP; i++) {
-        s.gq_count[i] = (i == s.gq_n) ? (int)(int16_t)amount : s.gq_count[i];
-        s.gq_delay[i] = (i == s.gq_n) ? t + 1000 : s.gq_delay[i];
-    }
+template <int S> B2T_HD void gq_add(PS& s, int amount, int32_t t) {  // :22-24
+    if (s.gq_n >= GQ_CAP) { s.flags |= 1; return; }  // sticky overflow, surfaced through b2t_stats
+    gq_set_count<S>(s, s.gq_n, (int16_t)amount);
+    gq_set_delay<S>(s, s.gq_n, t + 1000);
     s.gq_n++;
 }
-B2T_HD int gq_block(PS& s, int amount, int32_t t, bool freeze) {  // :26-52
+template <int S> B2T_HD int gq_block(PS& s, int amount, int32_t t, bool freeze) {  // :26-52
     amount &= 0xFFFF;
     if (s.gq_n == 0) return amount;
-    const int32_t delay = s.gq_delay[0];
+    const int32_t delay = gq_delay_at<S>(s, 0);
     while (amount && s.gq_n) {
-        s.gq_count[0]--;
+        const int c = gq_count_at<S>(s, 0) - 1;
+        gq_set_count<S>(s, 0, c);
         amount--;
-        if (s.gq_count[0] == 0) gq_pop(s);
+        if (c == 0) gq_pop<S>(s);
     }
     if (s.gq_n) {
-        if (delay > s.gq_delay[0]) s.gq_delay[0] = delay;
+        int32_t d = gq_delay_at<S>(s, 0);
+        if (delay > d) d = delay;
         if (freeze) {
-            const int32_t a = s.gq_delay[0] + 450, b = t + s.min_remaining + 450;
-            s.gq_delay[0] = a < b ? a : b;
+            const int32_t a = d + 450, b = t + s.min_remaining + 450;
+            d = a < b ? a : b;
         }
+        gq_set_delay<S>(s, 0, d);
     } else s.min_remaining = 1000;
     return amount;
 }
-B2T_HD bool gq_check(PS& s, int32_t t) {  // :54-72 (addDelay is the constant 450 of :7)
+template <int S> B2T_HD bool gq_check(PS& s, int32_t t) {  // :54-72 (addDelay is the constant 450 of :7)
     if (s.gq_n == 0) return false;
-    if (t > s.gq_delay[0]) {
-        const int32_t delay = s.gq_delay[0] + 450;
-        if (--s.gq_count[0] == 0) gq_pop(s);
+    const int32_t front = gq_delay_at<S>(s, 0);
+    if (t > front) {
+        const int32_t delay = front + 450;
+        const int c = gq_count_at<S>(s, 0) - 1;
+        gq_set_count<S>(s, 0, c);
+        if (c == 0) gq_pop<S>(s);
         if (s.gq_n) {
-            if (delay > s.gq_delay[0]) s.gq_delay[0] = delay;
-            s.min_remaining = s.gq_delay[0] - t;
+            int32_t d = gq_delay_at<S>(s, 0);
+            if (delay > d) { d = delay; gq_set_delay<S>(s, 0, d); }
+            s.min_remaining = d - t;
         } else s.min_remaining = 1000;
         return true;
     }
-    const int32_t rem = s.gq_delay[0] - t;
+    const int32_t rem = front - t;
     if (rem < s.min_remaining) s.min_remaining = rem;
     return false;
 }
@@ -539,10 +545,10 @@ template <class G, int S> B2T_HD bool make_new_piece(PS& s, const Board<G, S>& b
     return false;
 }
 // gamePlay.cpp:160-171 sendLines
-B2T_HD int send_lines(PS& s, int lines) {
+template <int S> B2T_HD int send_lines(PS& s, int lines) {
     s.pending = (s.pending + lines) & 0xFFFF;
     if (lines == 0) { s.combo_time -= 200; return 0; }  // Combo.cpp:50-52
-    const int amount = gq_block(s, lines - 1, s.time_ms, true);
+    const int amount = gq_block<S>(s, lines - 1, s.time_ms, true);
     cb_increase(s, s.time_ms, lines);
     return amount;
 }
@@ -556,7 +562,7 @@ template <class G, int S> B2T_HD void hd_make(PS& s, const Board<G, S>& b, const
 }
 // gamePlay.cpp:54-59 hd_finish: -1 = died
 template <class G, int S> B2T_HD int hd_finish(PS& s, const Board<G, S>& b, const Tabs& tb, uint32_t seed16) {
-    const int sent = send_lines(s, clear_lines<G, S>(b, s.y));
+    const int sent = send_lines<S>(s, clear_lines<G, S>(b, s.y));
     if (make_new_piece<G, S>(s, b, tb, seed16)) return -1;
     return sent;
 }
@@ -589,10 +595,10 @@ template <class G, int S> B2T_HD int delay_check(PS& s, const Board<G, S>& b, co
         hd_make<G, S>(s, b, tb);                                                        // gamePlay.cpp:38-46 hd()
         return hd_finish<G, S>(s, b, tb, seed16);
     }
-    if (s.incoming >= 1) { gq_add(s, s.incoming, s.time_ms); s.incoming = 0; }
+    if (s.incoming >= 1) { gq_add<S>(s, s.incoming, s.time_ms); s.incoming = 0; }
     int sent = cb_check(s, s.time_ms, tb);
-    if (sent) sent = gq_block(s, sent, s.time_ms, false);
-    if (gq_check(s, s.time_ms))
+    if (sent) sent = gq_block<S>(s, sent, s.time_ms, false);
+    if (gq_check<S>(s, s.time_ms))
         if (push_garbage<G, S>(s, b, tb, seed16)) return -1;
     return sent;
 }
@@ -679,7 +685,7 @@ B2T_HD bool finish_actions(PS& p0, const Board<G, S>& b0, PS& p1, const Board<G,
             if (sent) p1.incoming += sent;
             alive++;
             p0.reward = p0.pending & 255; p0.pending = 0;
-            p0.inc_count = gq_total(p0) & 255;
+            p0.inc_count = gq_total<S>(p0) & 255;
         }
     }
     if (!p1.dead) {
@@ -689,7 +695,7 @@ B2T_HD bool finish_actions(PS& p0, const Board<G, S>& b0, PS& p1, const Board<G,
             if (sent) p0.incoming += sent;
             alive++;
             p1.reward = p1.pending & 255; p1.pending = 0;
-            p1.inc_count = gq_total(p1) & 255;
+            p1.inc_count = gq_total<S>(p1) & 255;
         }
     }
     if (alive < 2) { gf |= GF_ROUND_OVER; return true; }
@@ -699,9 +705,8 @@ B2T_HD bool finish_actions(PS& p0, const Board<G, S>& b0, PS& p1, const Board<G,
 // gamePlay.cpp:206-216 restartRound (+ what it does NOT clear) and :218-230 seed via the stream table
 template <class G, int S> B2T_HD void restart_and_seed(PS& s, const Board<G, S>& b, const Tabs& tb, uint32_t seed16) {
     board_clear<G, S>(b);
-    s.gq_n = 0; s.min_remaining = 1000;
-#pragma unroll
-    for (int i = 0; i < GQ_CAP; i++) { s.gq_count[i] = 0; s.gq_delay[i] = 0; }
+    gq_clear<S>(s);
+    s.min_remaining = 1000;
     s.combo_start = 0; s.combo_time = 0; s.combo_count = 0; s.line_count = 0;
     s.pending = 0;
     s.drop_delay = 1000; s.drop_delay_time = 0; s.inc_dd_time = 0; s.lockdown_time = 0; s.lockdown = 0;

@@ -21,6 +21,10 @@ template <class G, int S> struct Game {
 template <class G, int S> B2T_HD void game_put_word(Game<G, S>& g, int i, uint32_t w) {
     const int pl = i / G::PW, k = i % G::PW;
     if (pl >= 2) return;
+    if (k >= G::W * G::CW + G::SW + 14 && k < G::W * G::CW + G::SW + 14 + GQ_WORDS) {   // garbage queue: straight to its words
+        g.p[pl].gq[(k - (G::W * G::CW + G::SW + 14)) * S] = w;
+        return;
+    }
     if (k < G::W * G::CW) {
         if (G::CW == 1) g.b[pl].col(k) = (typename G::col_t)w;
         else reinterpret_cast<uint32_t*>(&g.b[pl].col(k >> 1))[k & 1] = w;
@@ -30,6 +34,8 @@ template <class G, int S> B2T_HD void game_put_word(Game<G, S>& g, int i, uint32
 template <class G, int S> B2T_HD uint32_t game_get_word(const Game<G, S>& g, int i) {
     const int pl = i / G::PW, k = i % G::PW;
     if (pl >= 2) return 0u;
+    if (k >= G::W * G::CW + G::SW + 14 && k < G::W * G::CW + G::SW + 14 + GQ_WORDS)
+        return g.p[pl].gq[(k - (G::W * G::CW + G::SW + 14)) * S];
     if (k < G::W * G::CW) {
         if (G::CW == 1) return (uint32_t)g.b[pl].col(k);
         return reinterpret_cast<const uint32_t*>(&g.b[pl].col(k >> 1))[k & 1];
@@ -37,7 +43,11 @@ template <class G, int S> B2T_HD uint32_t game_get_word(const Game<G, S>& g, int
     if (k < G::W * G::CW + G::SW) return g.b[pl].sw(k - G::W * G::CW);
     return g.sc[pl][k - G::W * G::CW - G::SW];
 }
-template <class G, int S> B2T_HD void game_unpack(Game<G, S>& g) { ps_unpack(g.p[0], g.sc[0]); ps_unpack(g.p[1], g.sc[1]); }
+template <class G, int S> B2T_HD void game_unpack(Game<G, S>& g) {   // keeps the queue pointers set by the caller
+    uint32_t* q0 = g.p[0].gq; uint32_t* q1 = g.p[1].gq;
+    ps_unpack(g.p[0], g.sc[0]); ps_unpack(g.p[1], g.sc[1]);
+    g.p[0].gq = q0; g.p[1].gq = q1;
+}
 template <class G, int S> B2T_HD void game_pack(Game<G, S>& g) { ps_pack(g.p[0], g.sc[0]); ps_pack(g.p[1], g.sc[1]); }
 
 // A never-reset game (b2t_create): empty boards, no piece, everybody alive
@@ -45,6 +55,7 @@ template <class G, int S> B2T_HD void game_init(Game<G, S>& g) {
     for (int pl = 0; pl < 2; pl++) {
         board_clear<G, S>(g.b[pl]);
         for (int k = 0; k < SCALAR_WORDS; k++) g.sc[pl][k] = 0;
+        for (int j = 0; j < GQ_WORDS; j++) g.p[pl].gq[j * S] = 0u;
     }
     game_unpack(g);
     for (int pl = 0; pl < 2; pl++) { g.p[pl].kind = 7; g.p[pl].min_remaining = 1000; g.p[pl].drop_delay = 1000; }

@@ -74,24 +74,31 @@ struct KParams {
     DevTabs tabs;
 };
 
+// Shared memory of the game kernel: one private region per warp, every array laid out [index][lane] (stride 32 words:
+// bank = lane, conflict-free for any per-thread index).  The output staging buffers reuse the warp's column area, which is
+// dead once the state has been written back, so only __syncwarp() is ever needed.
+constexpr int WS = 32;   // stride of all per-thread arrays
 template <class G> struct SmemLayout {
     typedef typename G::col_t col_t;
     static constexpr int HW = G::H * G::W;
     static constexpr int WB = 2 * HW;                         // words of packed field bits per warp (32 rows x 2HW bits)
-    static constexpr int COLS = 2 * G::NCOL * TPB * (int)sizeof(col_t);
-    static constexpr int STREAM = 2 * G::SW * TPB * 4;
-    static constexpr int BITS = WARPS * (WB + 1) * 4;
-    static constexpr int VEC = WARPS * 32 * 2 * VEC_LEN;
+    static constexpr int COLS = 2 * G::NCOL * WS * (int)sizeof(col_t);
+    static constexpr int STREAM = 2 * G::SW * WS * 4;
+    static constexpr int KEYS = G::KEYW * WS * 4;             // the acting player's packed key string
+    static constexpr int GQ = 2 * GQ_WORDS * WS * 4;          // both players' garbage queues
+    static constexpr int BITS = (((WB + 1) * 4 + 15) / 16) * 16;   // staging (aliases COLS): packed field bits of 32 rows
+    static constexpr int VEC = 32 * 2 * VEC_LEN;                    // staging (aliases COLS): 32 rows x 38 bytes
+    static_assert(BITS + VEC <= COLS, "output staging must fit in the warp's column area");
+    static constexpr int O_STREAM = COLS, O_KEYS = O_STREAM + STREAM, O_GQ = O_KEYS + KEYS;
+    static constexpr int WARP_BYTES = ((O_GQ + GQ + 15) / 16) * 16;
     static constexpr int TAB = 64 * 2;
-    static constexpr int KEYS = G::KEYW * TPB * 4;            // the acting player's packed key string, word j at [j][tid]
-    static constexpr int VEC16 = ((VEC + 15) / 16) * 16;
-    static constexpr int GAME_TOTAL = COLS + STREAM + BITS + VEC16 + KEYS + TAB;
+    static constexpr int GAME_TOTAL = WARPS * WARP_BYTES + TAB;
 };
 
 // ---------------------------------------------------------------------------------------------- cooperative outputs
 // wb: this warp's WB(+1) words.  Rows = lanes.  out = address of the warp's first row.
 template <class G>
-__device__ __forceinline__ void emit_fields(uint32_t* wb, const Board<G, TPB>& b0, const Board<G, TPB>& b1, bool has_row,
+__device__ __forceinline__ void emit_fields(uint32_t* wb, const Board<G, WS>& b0, const Board<G, WS>& b1, bool has_row,
                                             uint8_t* out, int valid_rows, int lane) {
     constexpr int HW = G::H * G::W;
     constexpr int REM = HW & 31;                 // valid bits in a player's last stream word (0 = all 32)
@@ -113,6 +120,7 @@ __device__ __forceinline__ void emit_fields(uint32_t* wb, const Board<G, TPB>& b
             }
         }
     }
+    __syncwarp();   // the staging words alias the warp's columns: every lane must be done with its board
     // 2. place it at bit lane*2*HW of the warp's stream: shift by sh, first/last words are shared with the neighbours
     const int bit0 = lane * 2 * HW, wo = bit0 >> 5, sh = bit0 & 31;
     const int nbit0 = bit0 + 2 * HW, nsh = nbit0 & 31, nidx = (nbit0 >> 5) - wo;   // next lane's first word, relative
@@ -193,6 +201,7 @@ __device__ __forceinline__ void vec_words(const PS& s, uint32_t* w) {
     w[4] = (uint32_t)(ohk >> 32);
 }
 __device__ __forceinline__ void emit_vecs(uint8_t* sv, const PS& p0, const PS& p1, bool has_row, uint8_t* out, int valid_rows, int lane) {
+    __syncwarp();   // staging aliases the warp's columns
     if (has_row) {
         uint32_t a[5], b[5], r[10];
         vec_words(p0, a);
@@ -244,15 +253,15 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
     typedef SmemLayout<G> L;
     constexpr int KW = G::KEYW;
     extern __shared__ __align__(16) unsigned char smem[];
-    col_t* s_cols = reinterpret_cast<col_t*>(smem);
-    uint32_t* s_stream = reinterpret_cast<uint32_t*>(smem + L::COLS);
-    uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem + L::COLS + L::STREAM);
-    uint8_t* s_vec = smem + L::COLS + L::STREAM + L::BITS;
-    uint32_t* s_keys = reinterpret_cast<uint32_t*>(smem + L::COLS + L::STREAM + L::BITS + L::VEC16);
-    uint16_t* s_tab = reinterpret_cast<uint16_t*>(smem + L::COLS + L::STREAM + L::BITS + L::VEC16 + L::KEYS);
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t* kw = s_keys + tid;                             // kw[j * TPB]
+    unsigned char* wbase = smem + warp * L::WARP_BYTES;
+    col_t* s_cols = reinterpret_cast<col_t*>(wbase);
+    uint32_t* s_stream = reinterpret_cast<uint32_t*>(wbase + L::O_STREAM);
+    uint32_t* kw = reinterpret_cast<uint32_t*>(wbase + L::O_KEYS) + lane;   // kw[j * WS]
+    uint32_t* s_gq = reinterpret_cast<uint32_t*>(wbase + L::O_GQ);
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(wbase);                  // staging, valid once the columns are dead
+    uint8_t* s_vec = wbase + L::BITS;
+    uint16_t* s_tab = reinterpret_cast<uint16_t*>(smem + WARPS * L::WARP_BYTES);
     const int row = blockIdx.x * TPB + tid;
     if (tid < 28) { s_tab[tid] = p.tabs.pcn[tid]; s_tab[32 + tid] = p.tabs.pcc[tid]; }
     Tabs tb;
@@ -260,12 +269,13 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
     tb.piece = p.tabs.piece; tb.hole = p.tabs.hole; tb.powtab = p.tabs.powtab;
     tb.piece_len = p.tabs.piece_len; tb.hole_len = p.tabs.hole_len; tb.spawn_rots = p.tabs.spawn_rots;
 
-    Game<G, TPB> g;
+    Game<G, WS> g;
 #pragma unroll
     for (int pl = 0; pl < 2; pl++) {
-        g.b[pl].cols = s_cols + pl * G::NCOL * TPB + tid;
-        g.b[pl].stream = s_stream + pl * G::SW * TPB + tid;
-        board_init_walls<G, TPB>(g.b[pl]);
+        g.b[pl].cols = s_cols + pl * G::NCOL * WS + lane;
+        g.b[pl].stream = s_stream + pl * G::SW * WS + lane;
+        g.p[pl].gq = s_gq + pl * GQ_WORDS * WS + lane;
+        board_init_walls<G, WS>(g.b[pl]);
     }
     __syncthreads();
 
@@ -303,7 +313,7 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
             if (p.poke_player == 0) g.p[0].dead = p.poke_value; else g.p[1].dead = p.poke_value;
         }
         if (p.flags & KF_CLEAR_FIELD) {
-            if (p.poke_player == 0) board_clear<G, TPB>(g.b[0]); else board_clear<G, TPB>(g.b[1]);
+            if (p.poke_player == 0) board_clear<G, WS>(g.b[0]); else board_clear<G, WS>(g.b[1]);
         }
         if (p.flags & (KF_STEP | KF_EXPAND)) {
             const int player = p.player[i] ? 1 : 0;
@@ -318,7 +328,7 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
                 for (int j = 0; j < KW / 4; j++) {
                     uint4 q = src[j];
                     if (!valid) q = make_uint4(0u, 0u, 0u, 0u);
-                    kw[(4 * j) * TPB] = q.x; kw[(4 * j + 1) * TPB] = q.y; kw[(4 * j + 2) * TPB] = q.z; kw[(4 * j + 3) * TPB] = q.w;
+                    kw[(4 * j) * WS] = q.x; kw[(4 * j + 1) * WS] = q.y; kw[(4 * j + 2) * WS] = q.z; kw[(4 * j + 3) * WS] = q.w;
                     // sequences hold no zero token (except the null action): length = position of the last non-zero nibble
                     if (q.x) nkeys = (4 * j) * 8 + (msb32(q.x) >> 2) + 1;
                     if (q.y) nkeys = (4 * j + 1) * 8 + (msb32(q.y) >> 2) + 1;
@@ -339,19 +349,19 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
                             a = squeeze_keys(q.x) | (squeeze_keys(q.y) << 16);
                             b = squeeze_keys(q.z) | (squeeze_keys(q.w) << 16);
                         }
-                        kw[(2 * j) * TPB] = a; kw[(2 * j + 1) * TPB] = b;
+                        kw[(2 * j) * WS] = a; kw[(2 * j + 1) * WS] = b;
                     }
                 } else {
                     uint32_t tmp[KW];
                     pack_keys<KW>(kp, nkeys, tmp);
 #pragma unroll
-                    for (int j = 0; j < KW; j++) kw[j * TPB] = tmp[j];
+                    for (int j = 0; j < KW; j++) kw[j * WS] = tmp[j];
                 }
             }
             const bool was_over = (g.gf() & GF_ROUND_OVER) != 0;
             const bool finalize = (p.flags & KF_FINALIZE) != 0;
             int rew;
-            const bool done = game_perform<G, TPB, TPB>(g, tb, player, kw, nkeys, finalize, p.elapsed, &rew);
+            const bool done = game_perform<G, WS, WS>(g, tb, player, kw, nkeys, finalize, p.elapsed, &rew);
             if (p.reward) p.reward[row] = (int8_t)rew;
             if (p.done) p.done[row] = done ? 1 : 0;
             if (p.lines) *reinterpret_cast<uint16_t*>(p.lines + 2 * (size_t)row) = (uint16_t)((g.p[0].reward & 255) | ((g.p[1].reward & 255) << 8));
@@ -364,7 +374,7 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
                     for (int c = 0; c < KW / 2; c++) {          // 16 keys (two packed words) per 128-bit store
                         if (16 * c < p.lmax_out) {
                             uint4 q;
-                            const uint32_t k0 = kw[(2 * c) * TPB], k1 = kw[(2 * c + 1) * TPB];
+                            const uint32_t k0 = kw[(2 * c) * WS], k1 = kw[(2 * c + 1) * WS];
                             q.x = spread_nibbles(k0 & 0xFFFFu); q.y = spread_nibbles(k0 >> 16);
                             q.z = spread_nibbles(k1 & 0xFFFFu); q.w = spread_nibbles(k1 >> 16);
                             if (vec_ok) *reinterpret_cast<uint4*>(ko + 16 * c) = q;
@@ -423,9 +433,9 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
     int valid_rows = total_rows - warp_row0;
     valid_rows = valid_rows < 0 ? 0 : (valid_rows > 32 ? 32 : valid_rows);
     if (p.field && valid_rows > 0)
-        emit_fields<G>(s_bits + warp * (L::WB + 1), g.b[0], g.b[1], active, p.field + (size_t)warp_row0 * (size_t)(2 * L::HW), valid_rows, lane);
+        emit_fields<G>(s_bits, g.b[0], g.b[1], active, p.field + (size_t)warp_row0 * (size_t)(2 * L::HW), valid_rows, lane);
     if (p.vec && valid_rows > 0)
-        emit_vecs(s_vec + warp * 32 * 2 * VEC_LEN, g.p[0], g.p[1], active, p.vec + (size_t)warp_row0 * (size_t)(2 * VEC_LEN), valid_rows, lane);
+        emit_vecs(s_vec, g.p[0], g.p[1], active, p.vec + (size_t)warp_row0 * (size_t)(2 * VEC_LEN), valid_rows, lane);
     // ---- episode statistics: one atomic per non-zero counter per warp, spread over slices
     if (p.stats && (p.flags & KF_STEP)) {
         int vals[STAT_WORDS] = {st_steps, st_done, st_w0, st_w1, st_both, st_lines, st_gq, st_rng};
@@ -828,14 +838,15 @@ __global__ void __launch_bounds__(64) fill_tables_kernel(uint8_t* piece, uint32_
 template <class G>
 __global__ void __launch_bounds__(TPB) init_kernel(uint4* state, int n_games) {
     typedef typename G::col_t col_t;
+    typedef SmemLayout<G> L;
     extern __shared__ __align__(16) unsigned char smem[];
-    col_t* s_cols = reinterpret_cast<col_t*>(smem);
-    uint32_t* s_stream = reinterpret_cast<uint32_t*>(smem + SmemLayout<G>::COLS);
-    const int tid = threadIdx.x, gi = blockIdx.x * TPB + tid;
-    Game<G, TPB> g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gi = blockIdx.x * TPB + tid;
+    unsigned char* wbase = smem + warp * L::WARP_BYTES;
+    Game<G, WS> g;
     for (int pl = 0; pl < 2; pl++) {
-        g.b[pl].cols = s_cols + pl * G::NCOL * TPB + tid;
-        g.b[pl].stream = s_stream + pl * G::SW * TPB + tid;
+        g.b[pl].cols = reinterpret_cast<col_t*>(wbase) + pl * G::NCOL * WS + lane;
+        g.b[pl].stream = reinterpret_cast<uint32_t*>(wbase + L::O_STREAM) + pl * G::SW * WS + lane;
+        g.p[pl].gq = reinterpret_cast<uint32_t*>(wbase + L::O_GQ) + pl * GQ_WORDS * WS + lane;
     }
     if (gi >= n_games) return;
     game_init(g);
@@ -879,7 +890,7 @@ template <class G> struct Launch {
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(enumerate_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, EnumCfg<G>::SMEM);
         if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(init_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::COLS + L::STREAM);
+        return cudaFuncSetAttribute(init_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::GAME_TOTAL);
     }
     static cudaError_t game(const KParams& p, int rows, cudaStream_t s) {
         if (rows <= 0) return cudaSuccess;
@@ -899,7 +910,7 @@ template <class G> struct Launch {
         return cudaGetLastError();
     }
     static cudaError_t init(uint4* state, int n, cudaStream_t s) {
-        init_kernel<G><<<(n + TPB - 1) / TPB, TPB, L::COLS + L::STREAM, s>>>(state, n);
+        init_kernel<G><<<(n + TPB - 1) / TPB, TPB, L::GAME_TOTAL, s>>>(state, n);
         return cudaGetLastError();
     }
     static const GeomOps* ops() {

@@ -69,6 +69,7 @@ template <int H, int W> struct HS : HSBase {
     Tabs tb;
     col_t cols[2][G::NCOL];
     uint32_t stream[2][G::SW];
+    uint32_t gqw[2][GQ_WORDS];
 
     HS(int n_, const uint8_t* map_, uint32_t plen, uint32_t hlen) : n(n_), piece_len(plen), hole_len(hlen) {
         memcpy(map, map_, 7);
@@ -89,7 +90,7 @@ template <int H, int W> struct HS : HSBase {
     }
     void bind(Game<G, 1>& g) {
         for (int p = 0; p < 2; p++) {
-            g.b[p].cols = cols[p]; g.b[p].stream = stream[p];
+            g.b[p].cols = cols[p]; g.b[p].stream = stream[p]; g.p[p].gq = gqw[p];
             board_init_walls<G, 1>(g.b[p]);
         }
     }
