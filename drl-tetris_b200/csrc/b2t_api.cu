@@ -58,8 +58,8 @@ struct b2t_handle {
     int32_t* kcache = nullptr;
     int32_t* scan_sums = nullptr;
     int32_t* d_total = nullptr;
-    int32_t* row_board = nullptr;   // expand: row -> board map when the caller does not ask for it
-    size_t row_board_cap = 0;
+    int4* row_meta = nullptr;       // expand: {board slot, game, placement, player} of every output row
+    size_t row_meta_cap = 0;
     uint8_t* piece_tab = nullptr;
     uint8_t* hole_tab = nullptr;
     double* powtab = nullptr;
@@ -94,7 +94,7 @@ int b2t_destroy(b2t_handle* h) {
     cudaSetDevice(h->cfg.device);
     cudaFree(h->state);
     for (auto s : h->snap) cudaFree(s);
-    cudaFree(h->plc); cudaFree(h->kcache); cudaFree(h->scan_sums); cudaFree(h->d_total); cudaFree(h->row_board);
+    cudaFree(h->plc); cudaFree(h->kcache); cudaFree(h->scan_sums); cudaFree(h->d_total); cudaFree(h->row_meta);
     cudaFree(h->piece_tab); cudaFree(h->hole_tab); cudaFree(h->powtab); cudaFree(h->stats); cudaFree(h->xfer);
     h->in.release(); h->out.release();
     delete h;
@@ -260,13 +260,12 @@ int b2t_enumerate(b2t_handle* h, const int32_t* d_idx, int32_t n, const uint8_t*
     return B2T_OK;
 }
 
-static int scan_offsets(b2t_handle* h, const int32_t* d_K, int n, int32_t* d_offsets, int32_t* d_row_board, int capacity, cudaStream_t s) {
+static int scan_offsets(b2t_handle* h, const int32_t* d_K, int n, int32_t* d_offsets, cudaStream_t s) {
     const int tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (tiles > SCAN_TILE) return fail(h, B2T_ERR_ARG, "b2t_expand: n too large for the offset scan%s");
     scan_tile_sums<<<tiles, SCAN_TPB, 0, s>>>(d_K, n, h->scan_sums);
     scan_sums<<<1, SCAN_TPB, 0, s>>>(h->scan_sums, tiles);
     scan_finish<<<tiles, SCAN_TPB, 0, s>>>(d_K, n, h->scan_sums, d_offsets);
-    if (d_row_board) fill_row_board<<<(n + 255) / 256, 256, 0, s>>>(d_offsets, n, d_row_board, capacity);
     CK(cudaGetLastError());
     return B2T_OK;
 }
@@ -278,22 +277,20 @@ int b2t_expand(b2t_handle* h, const b2t_expand_args* a, void* stream) {
     if (int r = check_obs(h, a->obs)) return r;
     cudaStream_t s = (cudaStream_t)stream;
     if (int r = b2t_enumerate(h, a->d_game_idx, a->n, a->d_player, a->d_K, nullptr, nullptr, 0, 0, stream)) return r;
-    int32_t* row_board = a->d_board;
-    if (!row_board) {
-        if (h->row_board_cap < (size_t)a->capacity) {
-            CK(cudaFree(h->row_board));
-            h->row_board = nullptr; h->row_board_cap = 0;
-            CK(cudaMalloc((void**)&h->row_board, ((size_t)a->capacity + 1) * sizeof(int32_t)));
-            h->row_board_cap = (size_t)a->capacity;
-        }
-        row_board = h->row_board;
+    if (h->row_meta_cap < (size_t)a->capacity) {
+        CK(cudaFree(h->row_meta));
+        h->row_meta = nullptr; h->row_meta_cap = 0;
+        CK(cudaMalloc((void**)&h->row_meta, ((size_t)a->capacity + 1) * sizeof(int4)));
+        h->row_meta_cap = (size_t)a->capacity;
     }
-    if (int r = scan_offsets(h, a->d_K, a->n, a->d_offsets, row_board, a->capacity, s)) return r;
+    if (int r = scan_offsets(h, a->d_K, a->n, a->d_offsets, s)) return r;
+    fill_row_meta<<<(a->n + 255) / 256, 256, 0, s>>>(a->d_offsets, a->n, a->d_game_idx, a->d_player, h->row_meta, a->d_board, a->capacity);
+    CK(cudaGetLastError());
     KParams p; base_params(h, p);
     p.idx = a->d_game_idx; p.n = a->n; p.player = a->d_player;
     p.flags = KF_EXPAND | (a->finalize ? KF_FINALIZE : 0u);
     if (a->time_ms > 0) p.elapsed = a->time_ms;
-    p.offsets = a->d_offsets; p.capacity = a->capacity; p.row_board = row_board;
+    p.offsets = a->d_offsets; p.capacity = a->capacity; p.row_meta = h->row_meta;
     p.reward = a->d_reward; p.done = a->d_done; p.lines = a->d_lines;
     p.keys_out = a->d_keys; p.key_len_out = a->d_key_len; p.lmax_out = a->lmax;
     set_obs(p, a->obs);

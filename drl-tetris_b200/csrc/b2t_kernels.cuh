@@ -55,7 +55,7 @@ struct KParams {
     int32_t elapsed;
     const uint32_t* reset_seeds;  // fused reset of finished games
     const int32_t* offsets;       // KF_EXPAND: [n+1]
-    const int32_t* row_board;     // KF_EXPAND: [capacity] board slot of every row (filled by scan_finish)
+    const int4* row_meta;         // KF_EXPAND: [capacity] {board slot i, game id, placement k, player} of every row
     int32_t capacity;
     int32_t poke_player, poke_value;
     // outputs (row-indexed)
@@ -280,21 +280,37 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
     __syncthreads();
 
     const bool expand = (p.flags & KF_EXPAND) != 0;
+    const bool stepping = (p.flags & (KF_STEP | KF_EXPAND)) != 0;
     int total_rows = p.n, i = row, k = 0;
     if (expand) {
         total_rows = p.offsets[p.n];
         if (total_rows > p.capacity) total_rows = p.capacity;
-        if (row < total_rows) {
-            i = p.row_board[row];
-            k = row - p.offsets[i];
-        }
     }
     const bool active = row < total_rows;
     // per-thread stat contributions
     int st_steps = 0, st_done = 0, st_w0 = 0, st_w1 = 0, st_both = 0, st_lines = 0, st_gq = 0, st_rng = 0;
 
     if (active) {
-        const int gi = p.idx ? p.idx[i] : i;
+        // ---- every global load that does not depend on the state is issued before the state itself
+        int gi, player = 0, sel = 0, nkeys = 0;
+        if (expand) {
+            const int4 m = p.row_meta[row];
+            i = m.x; gi = m.y; k = m.z; player = m.w; sel = k;
+        } else {
+            gi = p.idx ? p.idx[i] : i;
+            if (stepping) {
+                player = p.player[i] ? 1 : 0;
+                if (p.placement) sel = p.placement[i]; else nkeys = p.key_len[i];
+            }
+        }
+        const bool by_cache = stepping && (expand || p.placement);
+        // fast path: key rows of 16 or 32 bytes, 16-byte aligned, fetched as one or two 128-bit loads
+        constexpr int KQ = 2;
+        const bool key_vec = stepping && !by_cache && (p.lmax == 16 || p.lmax == 32) && ((reinterpret_cast<uintptr_t>(p.keys) & 15) == 0);
+        // (issuing the key loads here, ahead of the state, or prefetching the piece-stream entries was measured slower: the extra
+        // live registers cost more than the exposed latency)
+        int kc = 0;
+        if (by_cache) kc = p.kcache[gi];
         {
             const uint4* src = p.state + gi;
 #pragma unroll
@@ -315,12 +331,8 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
         if (p.flags & KF_CLEAR_FIELD) {
             if (p.poke_player == 0) board_clear<G, WS>(g.b[0]); else board_clear<G, WS>(g.b[1]);
         }
-        if (p.flags & (KF_STEP | KF_EXPAND)) {
-            const int player = p.player[i] ? 1 : 0;
-            int nkeys;
-            if (expand || p.placement) {
-                int sel = expand ? k : p.placement[i];
-                const int kc = p.kcache[gi];
+        if (stepping) {
+            if (by_cache) {
                 const bool valid = sel >= 0 && sel < kc && sel < G::KMAX;   // out of range -> null action (action_list.py:27-33)
                 const uint4* src = reinterpret_cast<const uint4*>(p.plc + ((size_t)gi * G::KMAX + (valid ? sel : 0)) * KW);
                 nkeys = 1;
@@ -336,22 +348,25 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
                     if (q.w) nkeys = (4 * j + 3) * 8 + (msb32(q.w) >> 2) + 1;
                 }
             } else {
-                nkeys = p.key_len[i];
                 if (nkeys > KW * 8) nkeys = KW * 8;
                 if (nkeys > p.lmax) nkeys = p.lmax;
-                const uint8_t* kp = p.keys + (size_t)i * (size_t)p.lmax;
-                if ((p.lmax & 15) == 0 && ((reinterpret_cast<uintptr_t>(p.keys) & 15) == 0)) {
+                if (key_vec) {
+                    uint4 kq[KQ];
+                    {
+                        const uint8_t* kp = p.keys + (size_t)i * (size_t)p.lmax;
+#pragma unroll
+                        for (int j = 0; j < KQ; j++)
+                            kq[j] = (16 * j < p.lmax) ? *reinterpret_cast<const uint4*>(kp + 16 * j) : make_uint4(0u, 0u, 0u, 0u);
+                    }
 #pragma unroll
                     for (int j = 0; j < KW / 2; j++) {       // 16 keys per uint4 -> two packed words
-                        uint32_t a = 0u, b = 0u;
-                        if (16 * j < nkeys) {
-                            const uint4 q = *reinterpret_cast<const uint4*>(kp + 16 * j);
-                            a = squeeze_keys(q.x) | (squeeze_keys(q.y) << 16);
-                            b = squeeze_keys(q.z) | (squeeze_keys(q.w) << 16);
-                        }
-                        kw[(2 * j) * WS] = a; kw[(2 * j + 1) * WS] = b;
+                        const bool in = j < KQ && 16 * j < nkeys;
+                        const uint4 q = kq[j < KQ ? j : 0];
+                        kw[(2 * j) * WS] = in ? (squeeze_keys(q.x) | (squeeze_keys(q.y) << 16)) : 0u;
+                        kw[(2 * j + 1) * WS] = in ? (squeeze_keys(q.z) | (squeeze_keys(q.w) << 16)) : 0u;
                     }
                 } else {
+                    const uint8_t* kp = p.keys + (size_t)i * (size_t)p.lmax;
                     uint32_t tmp[KW];
                     pack_keys<KW>(kp, nkeys, tmp);
 #pragma unroll
@@ -800,14 +815,19 @@ __global__ void __launch_bounds__(SCAN_TPB) scan_sums(int32_t* sums, int tiles) 
     for (int j = 0; j < SCAN_ITEMS; j++) { if (base + j < tiles) sums[base + j] = ex; ex += v[j]; }
 }
 // phase 3: offsets
-// row -> board map for expand: one thread per board writes its K consecutive rows
-__global__ void __launch_bounds__(256) fill_row_board(const int32_t* offsets, int n, int32_t* row_board, int capacity) {
+// row -> {board slot, game id, placement, player} for expand: one thread per board writes its K consecutive rows
+__global__ void __launch_bounds__(256) fill_row_meta(const int32_t* offsets, int n, const int32_t* idx, const uint8_t* player,
+                                                     int4* row_meta, int32_t* row_board, int capacity) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int a = offsets[i];
     int b = offsets[i + 1];
     if (b > capacity) b = capacity;
-    for (int r = a; r < b; r++) row_board[r] = i;
+    const int gi = idx ? idx[i] : i, pl = player[i] ? 1 : 0;
+    for (int r = a; r < b; r++) {
+        row_meta[r] = make_int4(i, gi, r - a, pl);
+        if (row_board) row_board[r] = i;
+    }
 }
 __global__ void __launch_bounds__(SCAN_TPB) scan_finish(const int32_t* K, int n, const int32_t* sums, int32_t* offsets) {
     __shared__ int s_warp[32];
