@@ -621,27 +621,32 @@ template <class G, int S> B2T_HD void rotate_key(PS& s, const Board<G, S>& b, co
     }
     if (ok) { s.rot = nr; s.x = x; s.y = y; pcn_cur = pcn; }
 }
-template <class G, int S> B2T_HD void apply_key(PS& s, const Board<G, S>& b, const Tabs& tb, int key, uint32_t& pcn) {
-    if (key == 1 || key == 3) {
-        const int dx = key - 2;
-        if (fits<G, S>(b, s.x + dx, s.y, pcn)) s.x += dx;
-    } else if (key == 2 || key == 4) {
-        const int dx = key - 3;
-        while (fits<G, S>(b, s.x + dx, s.y, pcn)) s.x += dx;
-    } else if (key == 5 || key == 6) {          // GamePlay::mDown once / until blocked, with its DropDelay bookkeeping
-        bool moved;
-        do {
-            moved = fits<G, S>(b, s.x, s.y + 1, pcn);
-            if (moved) { s.y++; dd_reset(s, s.time_ms); } else dd_set(s, s.time_ms);
-        } while (moved && key == 6);
+// `run` consecutive copies of one key (PythonHandle.cpp:73-112).  Repeats are folded where the outcome allows it: a lateral
+// step that is blocked stays blocked, n single downs are one descent of min(n, free rows) with the same DropDelay
+// bookkeeping (reset after any successful step, set after the first failed one; DropDelay.cpp:23-41 is idempotent).
+template <class G, int S> B2T_HD void apply_key_run(PS& s, const Board<G, S>& b, const Tabs& tb, int key, int run, uint32_t& pcn) {
+    if (key >= 1 && key <= 4) {
+        const int dx = (key & 1) ? key - 2 : key - 3;            // 1,2 -> -1 ; 3,4 -> +1
+        const int steps = (key == 2 || key == 4) ? G::W : run;    // slam: until blocked
+        for (int k = 0; k < steps; k++) {
+            if (!fits<G, S>(b, s.x + dx, s.y, pcn)) break;
+            s.x += dx;
+        }
+    } else if (key == 5 || key == 6) {                            // GamePlay::mDown (gamePlay.cpp:61-69), once each / until blocked
+        const int dist = rest_from<G>(collide_mask<G, S>(b, s.x, pcc_of(tb, s.kind, s.rot)), s.y) - s.y;
+        const int want = (key == 6) ? dist + 1 : run;             // key 6 always ends with one failed step
+        const int d = want < dist ? want : dist;
+        if (d > 0) { s.y += d; dd_reset(s, s.time_ms); }
+        if (d < want) dd_set(s, s.time_ms);
     } else if (key >= 8 && key <= 10) {
-        rotate_key<G, S>(s, b, tb, key == 8 ? 1 : key == 9 ? 3 : 2, pcn);
+        for (int k = 0; k < run; k++) rotate_key<G, S>(s, b, tb, key == 8 ? 1 : key == 9 ? 3 : 2, pcn);
     } else if (key == 7) {
-        hd_make<G, S>(s, b, tb);
+        hd_make<G, S>(s, b, tb);                                   // locking twice in a row changes nothing
     }
 }
 // The acting player's whole key string (4-bit tokens, word j at keys[j*KS]).  Every enumerated placement ends with the hard
-// drop; it is peeled off the loop so that all lanes of a warp lock their piece together instead of once per distinct length.
+// drop; it is peeled off the loop so that all lanes of a warp lock their piece together instead of once per distinct length,
+// and the loop advances by runs of equal keys (the "n rows down" stretches of under-overhang placements are one step).
 template <class G, int S, int KS>
 B2T_HD void apply_keys(PS& s, const Board<G, S>& b, const Tabs& tb, const uint32_t* keys, int nkeys) {
     if (s.kind > 6 || nkeys <= 0) return;
@@ -649,12 +654,17 @@ B2T_HD void apply_keys(PS& s, const Board<G, S>& b, const Tabs& tb, const uint32
     const int last = nkeys - 1;
     const bool final_drop = ((keys[(last >> 3) * KS] >> (4 * (last & 7))) & 15u) == 7u;
     const int nloop = final_drop ? last : nkeys;
-    uint32_t cur = 0;
-    for (int i = 0; i < nloop; i++) {
-        if ((i & 7) == 0) cur = keys[(i >> 3) * KS];
-        const int key = (int)(cur & 15u);
-        cur >>= 4;
-        apply_key<G, S>(s, b, tb, key, pcn);
+    int i = 0;
+    while (i < nloop) {
+        const uint32_t w = keys[(i >> 3) * KS] >> (4 * (i & 7));   // this word from token i on (zeros shifted in above)
+        const uint32_t key = w & 15u;
+        const uint32_t diff = w ^ (key * 0x11111111u);              // zero nibbles where the token repeats
+        int run = diff ? (ctz32(diff) >> 2) : 8;
+        const int avail = 8 - (i & 7);
+        if (run > avail) run = avail;
+        if (run > nloop - i) run = nloop - i;
+        apply_key_run<G, S>(s, b, tb, (int)key, run, pcn);
+        i += run;
     }
     if (final_drop) hd_make<G, S>(s, b, tb);
 }
