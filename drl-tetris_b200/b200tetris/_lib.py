@@ -28,7 +28,7 @@ class Info(C.Structure):
 
 
 class Obs(C.Structure):
-    _fields_ = [("d_field", vp), ("d_vec", vp), ("d_piece_idx", vp), ("d_scalars", vp)]
+    _fields_ = [("d_field", vp), ("d_vec", vp), ("d_piece_idx", vp), ("d_scalars", vp), ("perspective", C.c_int32), ("d_me", vp)]
 
 
 class StepArgs(C.Structure):
@@ -53,6 +53,7 @@ SYMBOLS = {
     "b2t_observe": (C.c_int, [vp, vp, C.c_int32, C.POINTER(Obs), vp]),
     "b2t_enumerate": (C.c_int, [vp, vp, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_int32, vp]),
     "b2t_expand": (C.c_int, [vp, C.POINTER(ExpandArgs), vp]),
+    "b2t_select": (C.c_int, [vp, vp, vp, C.c_int32, vp, vp]),
     "b2t_snapshot": (C.c_int, [vp, C.c_int32, vp]),
     "b2t_restore": (C.c_int, [vp, C.c_int32, vp]),
     "b2t_export_state": (C.c_int, [vp, C.c_int32, vp, vp]),

@@ -205,13 +205,18 @@ class Engine:
         n = self.n if idx is None else idx.numel()
         self._ck(self.lib.b2t_reset(self._h, self._dp(idx), n, self._dp(seeds), self._stream()))
 
-    def _obs(self, field=None, vec=None, piece_idx=None, scalars=None):
+    def _obs(self, field=None, vec=None, piece_idx=None, scalars=None, perspective=False, me=None):
         o = _lib.Obs()
         o.d_field, o.d_vec, o.d_piece_idx, o.d_scalars = (self._dp(field), self._dp(vec), self._dp(piece_idx), self._dp(scalars))
+        o.perspective, o.d_me = int(bool(perspective)), self._dp(me)
         return o
 
+    def select_dev(self, scores, offsets, placement):
+        """argmax of per-placement scores within every board of the last expand_dev -> placement indices for step_dev"""
+        self._ck(self.lib.b2t_select(self._h, self._dp(scores), self._dp(offsets), placement.numel(), self._dp(placement), self._stream()))
+
     def step_dev(self, player, keys=None, key_len=None, idx=None, placement=None, finalize=True, time_ms=0, reset_seeds=None,
-                 reward=None, done=None, lines=None, field=None, vec=None, piece_idx=None, scalars=None):
+                 reward=None, done=None, lines=None, field=None, vec=None, piece_idx=None, scalars=None, perspective=False):
         a = _lib.StepArgs()
         a.d_game_idx = self._dp(idx)
         a.n = self.n if idx is None else idx.numel()
@@ -221,12 +226,12 @@ class Engine:
         a.finalize, a.time_ms = int(bool(finalize)), int(time_ms)
         a.d_reset_seeds = self._dp(reset_seeds)
         a.d_reward, a.d_done, a.d_lines = self._dp(reward), self._dp(done), self._dp(lines)
-        a.obs = self._obs(field, vec, piece_idx, scalars)
+        a.obs = self._obs(field, vec, piece_idx, scalars, perspective)
         self._ck(self.lib.b2t_step(self._h, C.byref(a), self._stream()))
 
-    def observe_dev(self, idx=None, field=None, vec=None, piece_idx=None, scalars=None):
+    def observe_dev(self, idx=None, field=None, vec=None, piece_idx=None, scalars=None, me=None):
         n = self.n if idx is None else idx.numel()
-        o = self._obs(field, vec, piece_idx, scalars)
+        o = self._obs(field, vec, piece_idx, scalars, me is not None, me)
         self._ck(self.lib.b2t_observe(self._h, self._dp(idx), n, C.byref(o), self._stream()))
 
     def enumerate_dev(self, player, K, idx=None, keys=None, key_len=None):
@@ -237,7 +242,7 @@ class Engine:
                                         kmax, lmax, self._stream()))
 
     def expand_dev(self, player, K, offsets, capacity, idx=None, finalize=True, time_ms=0, board=None, keys=None, key_len=None,
-                   reward=None, done=None, lines=None, field=None, vec=None, piece_idx=None):
+                   reward=None, done=None, lines=None, field=None, vec=None, piece_idx=None, perspective=False):
         a = _lib.ExpandArgs()
         a.d_game_idx = self._dp(idx)
         a.n = self.n if idx is None else idx.numel()
@@ -247,5 +252,5 @@ class Engine:
         a.d_keys, a.d_key_len = self._dp(keys), self._dp(key_len)
         a.lmax = keys.shape[1] if keys is not None else 0
         a.d_reward, a.d_done, a.d_lines = self._dp(reward), self._dp(done), self._dp(lines)
-        a.obs = self._obs(field, vec, piece_idx, None)
+        a.obs = self._obs(field, vec, piece_idx, None, perspective)
         self._ck(self.lib.b2t_expand(self._h, C.byref(a), self._stream()))

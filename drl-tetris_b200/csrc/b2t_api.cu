@@ -194,7 +194,10 @@ static int check_obs(b2t_handle* h, const b2t_obs& o) {
         return fail(h, B2T_ERR_ARG, "observation pointers must be 16-byte aligned%s");
     return B2T_OK;
 }
-static void set_obs(KParams& p, const b2t_obs& o) { p.field = o.d_field; p.vec = o.d_vec; p.piece_idx = o.d_piece_idx; p.scalars = o.d_scalars; }
+static void set_obs(KParams& p, const b2t_obs& o) {
+    p.field = o.d_field; p.vec = o.d_vec; p.piece_idx = o.d_piece_idx; p.scalars = o.d_scalars;
+    p.perspective = o.perspective ? 1 : 0; p.me = o.d_me;
+}
 
 int b2t_reset(b2t_handle* h, const int32_t* d_idx, int32_t n, const uint32_t* d_seeds, void* stream) {
     if (!h) return B2T_ERR_ARG;
@@ -229,6 +232,7 @@ int b2t_observe(b2t_handle* h, const int32_t* d_idx, int32_t n, const b2t_obs* o
     if (!h || !obs) return B2T_ERR_ARG;
     if (n < 0 || n > h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_observe: bad n%s");
     if (int r = check_obs(h, *obs)) return r;
+    if (obs->perspective && !obs->d_me) return fail(h, B2T_ERR_ARG, "b2t_observe: perspective order needs d_me%s");
     CK(cudaSetDevice(h->cfg.device));
     KParams p; base_params(h, p);
     p.idx = d_idx; p.n = n; p.flags = 0;
@@ -295,6 +299,14 @@ int b2t_expand(b2t_handle* h, const b2t_expand_args* a, void* stream) {
     p.keys_out = a->d_keys; p.key_len_out = a->d_key_len; p.lmax_out = a->lmax;
     set_obs(p, a->obs);
     CK(h->ops->launch_game(p, a->capacity, s));
+    return B2T_OK;
+}
+
+int b2t_select(b2t_handle* h, const float* d_scores, const int32_t* d_offsets, int32_t n, int32_t* d_placement, void* stream) {
+    if (!h || !d_scores || !d_offsets || !d_placement || n < 0) return fail(h, B2T_ERR_ARG, "b2t_select: NULL argument or n < 0%s");
+    CK(cudaSetDevice(h->cfg.device));
+    if (n) select_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_scores, d_offsets, n, d_placement);
+    CK(cudaGetLastError());
     return B2T_OK;
 }
 
@@ -476,6 +488,7 @@ int b2t_observe_host(b2t_handle* h, const int32_t* h_idx, int32_t n, uint8_t* h_
     pidx.dst = h_piece_idx; pidx.bytes = 2 * N; scal.dst = h_scalars; scal.bytes = 64 * N;
     if (int r = plan_out(h, {&field, &vec, &pidx, &scal})) return r;
     b2t_obs o;
+    memset(&o, 0, sizeof o);
     o.d_field = (uint8_t*)dev_out(h->out, field); o.d_vec = (uint8_t*)dev_out(h->out, vec);
     o.d_piece_idx = (uint8_t*)dev_out(h->out, pidx); o.d_scalars = (int32_t*)dev_out(h->out, scal);
     if (int r = b2t_observe(h, (const int32_t*)dev_in(h->in, idx), n, &o, nullptr)) return r;

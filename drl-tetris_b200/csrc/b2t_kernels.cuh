@@ -66,6 +66,8 @@ struct KParams {
     uint8_t* vec;
     uint8_t* piece_idx;
     int32_t* scalars;
+    int32_t perspective;          // 1: (me, opponent) order of the observation tensors
+    const uint8_t* me;            // per-row perspective player for plain observe
     int32_t* board_of;            // KF_EXPAND
     uint8_t* keys_out;
     uint8_t* key_len_out;
@@ -200,12 +202,16 @@ __device__ __forceinline__ void vec_words(const PS& s, uint32_t* w) {
     w[3] = (uint32_t)ohk;
     w[4] = (uint32_t)(ohk >> 32);
 }
-__device__ __forceinline__ void emit_vecs(uint8_t* sv, const PS& p0, const PS& p1, bool has_row, uint8_t* out, int valid_rows, int lane) {
+__device__ __forceinline__ void emit_vecs(uint8_t* sv, const PS& p0, const PS& p1, bool swap, bool has_row, uint8_t* out, int valid_rows, int lane) {
     __syncwarp();   // staging aliases the warp's columns
     if (has_row) {
         uint32_t a[5], b[5], r[10];
         vec_words(p0, a);
         vec_words(p1, b);
+        if (swap) {
+#pragma unroll
+            for (int j = 0; j < 5; j++) { const uint32_t t = a[j]; a[j] = b[j]; b[j] = t; }
+        }
         // 38-byte record = a (19 bytes) ++ b (19 bytes): b starts 3 bytes into word 4
         r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; r[3] = a[3];
         r[4] = (a[4] & 0xFFFFFFu) | (b[0] << 24);
@@ -289,6 +295,7 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
     const bool active = row < total_rows;
     // per-thread stat contributions
     int st_steps = 0, st_done = 0, st_w0 = 0, st_w1 = 0, st_both = 0, st_lines = 0, st_gq = 0, st_rng = 0;
+    int obs_player = 0;
 
     if (active) {
         // ---- every global load that does not depend on the state is issued before the state itself
@@ -303,6 +310,7 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
                 if (p.placement) sel = p.placement[i]; else nkeys = p.key_len[i];
             }
         }
+        obs_player = player;
         const bool by_cache = stepping && (expand || p.placement);
         // fast path: key rows of 16 or 32 bytes, 16-byte aligned, fetched as one or two 128-bit loads
         constexpr int KQ = 2;
@@ -431,7 +439,11 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
                 dst[(size_t)v * (size_t)p.n_games] = q;
             }
         }
-        if (p.piece_idx) *reinterpret_cast<uint16_t*>(p.piece_idx + 2 * (size_t)row) = (uint16_t)((g.p[0].kind & 255) | ((g.p[1].kind & 255) << 8));
+        if (p.piece_idx) {
+            const bool sw = p.perspective && (stepping ? (player != 0) : (p.me[row] != 0));
+            const int k0 = sw ? g.p[1].kind : g.p[0].kind, k1 = sw ? g.p[0].kind : g.p[1].kind;
+            *reinterpret_cast<uint16_t*>(p.piece_idx + 2 * (size_t)row) = (uint16_t)((k0 & 255) | ((k1 & 255) << 8));
+        }
         if (p.scalars) {
             int32_t* s = p.scalars + (size_t)row * 16;
 #pragma unroll
@@ -444,13 +456,15 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
         }
     }
     // ---- warp-cooperative observation tensors
+    bool swap = false;     // perspective order: the acting player first
+    if (p.perspective && active) swap = (stepping ? (obs_player != 0) : (p.me[row] != 0));
     const int warp_row0 = blockIdx.x * TPB + warp * 32;
     int valid_rows = total_rows - warp_row0;
     valid_rows = valid_rows < 0 ? 0 : (valid_rows > 32 ? 32 : valid_rows);
     if (p.field && valid_rows > 0)
-        emit_fields<G>(s_bits, g.b[0], g.b[1], active, p.field + (size_t)warp_row0 * (size_t)(2 * L::HW), valid_rows, lane);
+        emit_fields<G>(s_bits, swap ? g.b[1] : g.b[0], swap ? g.b[0] : g.b[1], active, p.field + (size_t)warp_row0 * (size_t)(2 * L::HW), valid_rows, lane);
     if (p.vec && valid_rows > 0)
-        emit_vecs(s_vec, g.p[0], g.p[1], active, p.vec + (size_t)warp_row0 * (size_t)(2 * VEC_LEN), valid_rows, lane);
+        emit_vecs(s_vec, g.p[0], g.p[1], swap, active, p.vec + (size_t)warp_row0 * (size_t)(2 * VEC_LEN), valid_rows, lane);
     // ---- episode statistics: one atomic per non-zero counter per warp, spread over slices
     if (p.stats && (p.flags & KF_STEP)) {
         int vals[STAT_WORDS] = {st_steps, st_done, st_w0, st_w1, st_both, st_lines, st_gq, st_rng};
@@ -815,6 +829,19 @@ __global__ void __launch_bounds__(SCAN_TPB) scan_sums(int32_t* sums, int tiles) 
     for (int j = 0; j < SCAN_ITEMS; j++) { if (base + j < tiles) sums[base + j] = ex; ex += v[j]; }
 }
 // phase 3: offsets
+// segmented argmax of the caller's per-placement scores: first maximum wins, like numpy.argmax
+__global__ void __launch_bounds__(256) select_kernel(const float* scores, const int32_t* offsets, int n, int32_t* placement) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int a = offsets[i], b = offsets[i + 1];
+    int best = 0;
+    float bv = (b > a) ? scores[a] : 0.f;
+    for (int r = a + 1; r < b; r++) {
+        const float v = scores[r];
+        if (v > bv) { bv = v; best = r - a; }
+    }
+    placement[i] = best;
+}
 // row -> {board slot, game id, placement, player} for expand: one thread per board writes its K consecutive rows
 __global__ void __launch_bounds__(256) fill_row_meta(const int32_t* offsets, int n, const int32_t* idx, const uint8_t* player,
                                                      int4* row_meta, int32_t* row_board, int capacity) {

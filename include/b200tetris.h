@@ -80,6 +80,12 @@ typedef struct {
     uint8_t *d_vec;        /* [rows, 2, 19]    x, y, incoming_lines, min(25000,combo_time+50)//100, combo_count, nextpiece 1-hot, piece 1-hot */
     uint8_t *d_piece_idx;  /* [rows, 2] */
     int32_t *d_scalars;    /* [rows, 2, 8] raw State views (PythonHandle.h:54-82): x,y,inc_lines,combo_time,combo_count,nextpiece,reward,dead */
+    /* Player order of axis 1 of d_field / d_vec / d_piece_idx.  0: player index (0, 1).  1: perspective order (me, opponent),
+     * the layout agents/agent_utils/state_unpack.py:35-58,88-137 feeds the networks ([..., :12] of d_vec is its `vector`,
+     * d_field its `visual`, d_piece_idx its `piece`): "me" is the acting player for b2t_step / b2t_expand and d_me[row] for
+     * b2t_observe.  d_scalars always stays in player-index order. */
+    int32_t perspective;
+    const uint8_t *d_me;   /* [rows], only read by b2t_observe when perspective == 1 */
 } b2t_obs;
 
 /* tetris_environment.perform_action for n games at once (tetris_environment.py:102-116; vector :79-86):
@@ -137,6 +143,12 @@ typedef struct {
     b2t_obs obs;               /* rows = placements */
 } b2t_expand_args;
 int b2t_expand(b2t_handle *h, const b2t_expand_args *a, void *stream);
+
+/* The select step of the actor loop (sventon_agent: evaluate every placement, act on the best): for every board of the last
+ * b2t_expand, the placement with the highest score, first one on ties like numpy.argmax.  d_scores [total] float32 in the row
+ * order of b2t_expand; d_placement [n] is what b2t_step takes as d_placement.  Asynchronous, no host round trip: enumerate ->
+ * expand -> (caller's network) -> select -> step can be captured in one CUDA graph. */
+int b2t_select(b2t_handle *h, const float *d_scores, const int32_t *d_offsets, int32_t n, int32_t *d_placement, void *stream);
 
 /* PythonHandle.copy() / PythonHandle.set() for the whole vector (PythonHandle.cpp:36-42; tetris_environment.py:165-176) */
 int b2t_snapshot(b2t_handle *h, int32_t slot, void *stream);

@@ -320,3 +320,83 @@ def _front_seeds(env, n):
     s = env._seeds(ids)
     env._episode[ids] += 1
     return s
+
+
+def test_perspective_order_and_select_in_a_cuda_graph():
+    """SURVEY §8f-1 building blocks: observation tensors in the (me, opponent) order of agents/agent_utils/state_unpack.py,
+    the segmented argmax over the caller's placement scores, and the whole enumerate -> expand -> select -> step chain
+    captured in one CUDA graph (no host round trip) reproducing the eager result."""
+    import torch
+    from b200tetris import Engine
+    n = 4096
+    dev = torch.device("cuda:0")
+    mk = lambda: Engine(n)
+    a, b = mk(), mk()
+    seeds = torch.from_numpy(harness.seeds_for(np.arange(n), np.zeros(n, int)).astype(np.int64)).to(dev).to(torch.int32)
+    a.reset_dev(seeds); b.reset_dev(seeds)
+    cap = n * 64
+    K = torch.empty(n, dtype=torch.int32, device=dev); offs = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    pf = torch.empty((cap, 2, 22, 10), dtype=torch.uint8, device=dev); pv = torch.empty((cap, 2, 19), dtype=torch.uint8, device=dev)
+    pp = torch.empty((cap, 2), dtype=torch.uint8, device=dev)
+    sel = torch.empty(n, dtype=torch.int32, device=dev)
+    done = torch.empty(n, dtype=torch.uint8, device=dev); reward = torch.empty(n, dtype=torch.int8, device=dev)
+    field = torch.empty((n, 2, 22, 10), dtype=torch.uint8, device=dev); vec = torch.empty((n, 2, 19), dtype=torch.uint8, device=dev)
+    pidx = torch.empty((n, 2), dtype=torch.uint8, device=dev)
+    player = torch.zeros(n, dtype=torch.uint8, device=dev)
+    scores = torch.empty(cap, dtype=torch.float32, device=dev)
+
+    def score_fn():   # a stand-in for the caller's value network: fewer filled cells of "me" in the top half + noise from the row index
+        me = pf[:, 0, :11].sum((1, 2)).to(torch.float32)
+        scores.copy_(-me + (torch.arange(cap, device=dev) % 7).to(torch.float32) * 0.01)
+
+    def chain(e):
+        e.expand_dev(player, K, offs, cap, field=pf, vec=pv, piece_idx=pp, perspective=True)
+        score_fn()
+        e.select_dev(scores, offs, sel)
+        e.step_dev(player, placement=sel, reward=reward, done=done, field=field, vec=vec, piece_idx=pidx, perspective=True)
+
+    # perspective order == swapped standard order
+    for t in range(6):
+        player.fill_(t & 1)
+        chain(a)
+        torch.cuda.synchronize()
+        f2 = torch.empty_like(field); v2 = torch.empty_like(vec); p2 = torch.empty_like(pidx)
+        a.observe_dev(field=f2, vec=v2, piece_idx=p2)
+        torch.cuda.synchronize()
+        if t & 1:
+            f2, v2, p2 = f2.flip(1), v2.flip(1), p2.flip(1)
+        assert torch.equal(f2, field) and torch.equal(v2, vec) and torch.equal(p2, pidx)
+        f3 = torch.empty_like(field)
+        a.observe_dev(field=f3, me=player)
+        torch.cuda.synchronize()
+        assert torch.equal(f3, field)
+        # select == numpy argmax per segment
+        o = offs.cpu().numpy(); s = scores.cpu().numpy(); want = np.array([np.argmax(s[o[i]:o[i + 1]]) for i in range(0, n, 97)])
+        assert np.array_equal(want, sel.cpu().numpy()[::97])
+        # eager twin
+        chain(b)
+    torch.cuda.synchronize()
+    ref_a = a.observe()
+    # graph-captured twin of two more plies
+    g = torch.cuda.CUDAGraph()
+    player.fill_(0)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        chain(a)               # warm-up on the side stream (allocations happen here, not during capture)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    a.restore(0) if False else None
+    chain(b)                   # keep b in lock-step with a (same ply, eager)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        chain(a)
+    torch.cuda.synchronize()
+    # capture does not execute: replay once for a, run once eagerly for b
+    g.replay()
+    chain(b)
+    torch.cuda.synchronize()
+    xa, xb = a.observe(), b.observe()
+    for u, v in zip(xa, xb):
+        assert np.array_equal(u, v)
+    a.close(); b.close()
