@@ -400,3 +400,91 @@ def test_perspective_order_and_select_in_a_cuda_graph():
     for u, v in zip(xa, xb):
         assert np.array_equal(u, v)
     a.close(); b.close()
+
+
+def test_edge_cases_through_the_abi():
+    """Empty and degenerate inputs, argument errors, finished / never-reset games, capacity reporting."""
+    import ctypes as C
+    import torch
+    from b200tetris import B2TError, Engine, _lib
+    # unsupported geometry / player count / bad arguments are reported, not crashed on
+    with pytest.raises(B2TError) as e:
+        Engine(4, 23, 11)
+    assert e.value.code == _lib.ERR_UNSUPPORTED
+    with pytest.raises(B2TError) as e:
+        Engine(4, n_players=3)
+    assert e.value.code == _lib.ERR_UNSUPPORTED
+    with pytest.raises(B2TError) as e:
+        Engine(0)
+    assert e.value.code == _lib.ERR_ARG
+    eng = Engine(5)
+    with pytest.raises(B2TError) as e:          # more rows than games
+        eng.reset(np.zeros(6, np.uint32), np.arange(6))
+    assert e.value.code == _lib.ERR_ARG
+    with pytest.raises(B2TError) as e:          # placement stepping before any enumerate
+        eng.step(np.zeros(5, np.uint8), placement=np.zeros(5, np.int32))
+    assert e.value.code == _lib.ERR_STATE
+    # a never-reset game has no piece: its list is the null action, stepping it is harmless
+    K, keys, klen = eng.enumerate(np.zeros(5, np.uint8))
+    assert (K == 1).all() and (klen[:, 0] == 1).all() and (keys[:, 0, 0] == 0).all()
+    # n == 0 everywhere
+    z8, z32 = np.zeros(0, np.uint8), np.zeros(0, np.int32)
+    eng.reset(np.zeros(0, np.uint32), z32)
+    r = eng.step(z8, np.zeros((0, 16), np.uint8), z8, z32)
+    assert all(x.shape[0] == 0 for x in r)
+    assert eng.observe(z32)[0].shape == (0, 2, 22, 10)
+    # single game, single-byte key rows (lmax = 1), zero-length key strings
+    lead = pyoracle.OracleVector(5)
+    s = harness.seeds_for(np.arange(5), np.zeros(5, int))
+    eng.reset(s); lead.reset(s)
+    for t in range(30):
+        one = np.array([t % 5], np.int32)
+        pl = np.array([t & 1], np.uint8)
+        keys = np.array([[7 if t % 3 else 0]], np.uint8)
+        ln = np.array([0 if t % 7 == 6 else 1], np.uint8)
+        ra, rb = lead.step(pl, keys, ln, one), eng.step(pl, keys, ln, one)
+        for x, y in zip(ra, rb):
+            assert np.array_equal(x, y)
+    for x, y in zip(lead.observe(), eng.observe()):
+        assert np.array_equal(x[..., :3] if x.ndim == 3 else x, y[..., :3] if y.ndim == 3 else y)
+    # play one game to the end, then keep stepping it: done stays set, reward is repeated, state frozen (PythonHandle.cpp:139,150)
+    g = np.array([2], np.int32)
+    keys = np.array([[7] + [0] * 15], np.uint8); ln = np.array([1], np.uint8)
+    for t in range(200):
+        pl = np.array([t & 1], np.uint8)
+        ra, rb = lead.step(pl, keys, ln, g), eng.step(pl, keys, ln, g)
+        assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
+        if ra[1][0]:
+            break
+    assert ra[1][0] == 1
+    frozen = eng.observe(g)
+    for t in range(3):
+        pl = np.array([t & 1], np.uint8)
+        ra, rb = lead.step(pl, keys, ln, g), eng.step(pl, keys, ln, g)
+        assert rb[1][0] == 1 and np.array_equal(ra[0], rb[0])
+    for x, y in zip(frozen, eng.observe(g)):
+        assert np.array_equal(x, y)
+    # out-of-range placement index acts as the null action (action_list.py:27-33); negative too
+    K, _, _ = eng.enumerate(np.zeros(5, np.uint8))
+    before = eng.observe()[0].copy()
+    eng.step(np.zeros(5, np.uint8), placement=np.array([K[0] + 5, -1, 10 ** 6, K[3], -7], np.int32), finalize=False)
+    assert np.array_equal(before, eng.observe()[0])
+    # expand reports the total even when the caller's capacity is too small, and fills what fits
+    o_full = eng.expand(np.zeros(5, np.uint8))
+    o_small = eng.expand(np.zeros(5, np.uint8), capacity=7)
+    assert o_small["total"] == o_full["total"] > 7
+    assert np.array_equal(o_small["field"][:7], o_full["field"][:7]) and np.array_equal(o_small["keys"][:7], o_full["keys"][:7])
+    # statistics are plain sums
+    st = eng.stats()
+    assert st["garbage_queue_overflow"] == 0 and st["env_steps"] > 0 and st["episodes"] >= 1
+    eng.close()
+    # the largest supported field with its longest key strings, and the smallest
+    for H, W, pieces in ((40, 20, ALL7), (10, 6, (0, 6)), (12, 5, (4,))):
+        v = _engine(3, H, W, pieces)
+        o = pyoracle.OracleVector(3, H, W, pieces)
+        s = harness.seeds_for(np.arange(3), np.zeros(3, int))
+        v.reset(s); o.reset(s)
+        a = o.enumerate(np.zeros(3, np.uint8), kmax=256, lmax=v.e.lmax)
+        b = v.enumerate(np.zeros(3, np.uint8), kmax=256, lmax=v.e.lmax)
+        for x, y in zip(a[:3], b[:3]):
+            assert np.array_equal(x, y)
