@@ -508,11 +508,11 @@ constexpr int ETPB = 64;              // threads per block of the enumerate kern
 constexpr int EWARPS = ETPB / 32;
 
 template <class G> struct EnumCfg {
-    static constexpr int CCAP = 64;                                  // candidate slots per thread between two pooled searches
+    static constexpr int CCAP = 32;                                  // candidate slots per thread between two pooled searches
     static constexpr int PER_COMBO = (G::H - 1) / 2;                 // resting heights differ by >= 2 and start at 2
     static constexpr int NCOMBO = 4 * G::W;
     static constexpr int ACAP = G::KMAX;                             // accepted finesse entries per board (cannot overflow before the list does)
-    static constexpr int RES = 128;                                  // pooled results buffered per warp between acceptances (smem: 7 blocks/SM)
+    static constexpr int RES = 192;                                  // pooled results buffered per warp between acceptances (smem: 7 blocks/SM)
     static constexpr int PCAP = EnumGeo<G>::PCAP;
     static constexpr int RSW = 1 + (PCAP + 3) / 4;                   // result slot: header word + the raw search path
     static_assert(NCOMBO <= 128, "topmask is 128 bits");
