@@ -73,6 +73,7 @@ template <int KW> struct SeqWriter {      // into a register Seq (host paths)
     bool bad;
     B2T_HD explicit SeqWriter(Seq<KW>& s_) : s(s_), bad(false) { s.clear(); }
     B2T_HD void put(uint32_t tok) { if (s.n < KW * 8) s.push(tok); else bad = true; }
+    B2T_HD void put_run(uint32_t tok, int count) { for (int i = 0; i < count; i++) put(tok); }
 };
 template <int KW, int WS = 1> struct WordWriter {     // into KW words (stride WS) in (shared) memory: dynamic word index costs nothing there
     uint32_t* w;
@@ -85,6 +86,18 @@ template <int KW, int WS = 1> struct WordWriter {     // into KW words (stride W
         acc |= tok << (4 * (n & 7));
         n++;
         if ((n & 7) == 0) { w[((n >> 3) - 1) * WS] = acc; acc = 0u; }
+    }
+    B2T_HD void put_run(uint32_t tok, int count) {   // `count` copies of one token, a word at a time
+        while (count > 0) {
+            if (n >= KW * 8) { bad = true; return; }
+            const int at = n & 7, room = 8 - at;
+            const int m = count < room ? count : room;
+            const uint32_t mask = (m == 8) ? 0xFFFFFFFFu : ((1u << (4 * m)) - 1u);
+            acc |= ((tok * 0x11111111u) & mask) << (4 * at);
+            n += m;
+            count -= m;
+            if ((n & 7) == 0) { w[((n >> 3) - 1) * WS] = acc; acc = 0u; }
+        }
     }
     B2T_HD void finish() {   // flush the partial word and zero the rest
         int j = n >> 3;
@@ -328,10 +341,10 @@ template <class G, int S, int KW, class Sink, int PST = 1> struct Enumerator {
         const int d = (brot - spawn) & 3;
         if (d) w.put(d == 1 ? 8u : d == 2 ? 10u : 9u);
         const int n = bx_ - G::SPAWN_X;
-        for (int i = 0; i < (n > 0 ? n : -n); i++) w.put(n > 0 ? 3u : 1u);
+        w.put_run(n > 0 ? 3u : 1u, n > 0 ? n : -n);
         for (int i = pn - 1; i >= 0; i--) {
             const uint32_t e = pb[i * PS2];
-            if (e >= 16u) for (uint32_t k = 16u; k < e; k++) w.put(5u);
+            if (e >= 16u) w.put_run(5u, (int)e - 16);
             else w.put(e);
         }
         w.put(7u);
