@@ -78,9 +78,19 @@ def load():
     """dlopen the in-tree library and type every symbol the header declares."""
     global _lib
     if _lib is None:
+        if not os.path.exists(LIB_PATH) and not os.environ.get("B2T_LIB"):
+            # a fresh checkout: compile the CUDA library in-tree (nvcc cross-compiles sm_100a without a GPU); never a CPU fallback
+            try:
+                import importlib.util
+                spec = importlib.util.spec_from_file_location("b2t_build", os.path.join(os.path.dirname(_HERE), "build.py"))
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                mod.build(verbose=False)
+            except Exception as e:  # noqa: BLE001
+                raise ImportError("b200tetris: %s is missing and could not be built (%s) — run `python drl-tetris_b200/build.py` "
+                                  "(nvcc, sm_100a).  There is no CPU fallback." % (LIB_PATH, e))
         if not os.path.exists(LIB_PATH):
-            raise ImportError("b200tetris: %s is missing — run `python drl-tetris_b200/build.py` (nvcc, sm_100a). "
-                              "There is no CPU fallback." % LIB_PATH)
+            raise ImportError("b200tetris: %s is missing.  There is no CPU fallback." % LIB_PATH)
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)   # AttributeError here = header/library mismatch

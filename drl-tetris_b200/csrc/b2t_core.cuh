@@ -362,49 +362,62 @@ template <class G, int S> B2T_HD void garbage_row(const Board<G, S>& b, int hole
 }
 
 // ------------------------------------------------------------------------------------------------ player scalars
+// A player's scalars IN REGISTERS ARE the 14 state words of the HBM layout: C bit-fields give every small field its name
+// while two players cost 28 registers instead of 54 and nothing is packed or unpacked.  (x86-64 and NVCC allocate bit-fields
+// from the least significant bit of 32-bit units, in declaration order.)
 struct PS {
-    int kind, rot, x, y, next, dead, lockdown;
-    int reward, inc_count, combo_count, line_count;
-    int remaining, pending;
+    // word 0
+    uint32_t kind : 3, rot : 2, next : 3;
+    int32_t x : 8, y : 8;
+    uint32_t dead : 1, lockdown : 1, : 6;
+    // word 1
+    uint32_t reward : 8, inc_count : 8, combo_count : 8, line_count : 8;
+    // word 2
+    uint32_t remaining : 16, pending : 16;
+    // words 3..5
     int32_t time_ms, combo_start, combo_time;
-    int drop_delay, incoming;
+    // word 6
+    uint32_t drop_delay : 16, incoming : 16;
+    // words 7..11
     int32_t drop_delay_time, inc_dd_time, lockdown_time, min_remaining;
     uint32_t piece_ctr;
-    int hole_ctr, hi12;  // hi12: p0 = seed16, p1 = game flags
-    int gq_n, flags;
+    // word 12   (hi12: player 0 = seed16, player 1 = game flags)
+    uint32_t hole_ctr : 16, hi12 : 16;
+    // word 13
+    uint32_t gq_n : 8, flags : 8, : 16;
     // GarbageHandler::garbage (Garbage.h:27): the queue is almost always empty, so it lives in (shared) memory, not in
-    // registers: 9 words, word j at gq[j*S]: 0..2 = six int16 counts, 3..8 = six int32 release times
+    // registers: 9 words, word j at gq[j*S]: 0..2 = six int16 counts, 3..8 = six int32 release times (state words 14..22)
     uint32_t* gq;
+};
+static_assert(sizeof(PS) >= 14 * 4, "PS must start with the 14 scalar state words");
+// The piece being moved by a key string, unpacked (the key loop touches these constantly)
+struct Cur {
+    int kind, rot, x, y, lockdown;
+    int32_t time_ms, drop_delay_time, lockdown_time;
 };
 constexpr int GQ_WORDS = 3 + GQ_CAP;   // state words 14..22 of a player
 // game flags (player 1, word 12 high half)
 constexpr int GF_ROUND_OVER = 1, GF_ENV_DONE = 2, GF_WINNER_SHIFT = 2, GF_GQ_OVERFLOW = 16, GF_RNG_OVERFLOW = 32;
 
+union PSWords {   // word view of the leading 14 words of PS
+    PS s;
+    uint32_t w[14];
+    B2T_HD PSWords() {}
+};
 B2T_HD void ps_unpack(PS& s, const uint32_t* w) {
-    s.kind = w[0] & 7; s.rot = (w[0] >> 3) & 3; s.next = (w[0] >> 5) & 7;
-    s.x = (int8_t)(w[0] >> 8); s.y = (int8_t)(w[0] >> 16); s.dead = (w[0] >> 24) & 1; s.lockdown = (w[0] >> 25) & 1;
-    s.reward = w[1] & 255; s.inc_count = (w[1] >> 8) & 255; s.combo_count = (w[1] >> 16) & 255; s.line_count = w[1] >> 24;
-    s.remaining = w[2] & 0xFFFF; s.pending = w[2] >> 16;
-    s.time_ms = (int32_t)w[3]; s.combo_start = (int32_t)w[4]; s.combo_time = (int32_t)w[5];
-    s.drop_delay = w[6] & 0xFFFF; s.incoming = w[6] >> 16;
-    s.drop_delay_time = (int32_t)w[7]; s.inc_dd_time = (int32_t)w[8]; s.lockdown_time = (int32_t)w[9];
-    s.min_remaining = (int32_t)w[10]; s.piece_ctr = w[11];
-    s.hole_ctr = w[12] & 0xFFFF; s.hi12 = w[12] >> 16;
-    s.gq_n = w[13] & 255; s.flags = (w[13] >> 8) & 255;
+    PSWords u;
+#pragma unroll
+    for (int i = 0; i < 14; i++) u.w[i] = w[i];
+    uint32_t* q = s.gq;
+    s = u.s;
+    s.gq = q;
 }
 B2T_HD void ps_pack(const PS& s, uint32_t* w) {
-    w[0] = (uint32_t)(s.kind & 7) | ((uint32_t)(s.rot & 3) << 3) | ((uint32_t)(s.next & 7) << 5) |
-           ((uint32_t)(s.x & 255) << 8) | ((uint32_t)(s.y & 255) << 16) | ((uint32_t)(s.dead & 1) << 24) |
-           ((uint32_t)(s.lockdown & 1) << 25);
-    w[1] = (uint32_t)(s.reward & 255) | ((uint32_t)(s.inc_count & 255) << 8) | ((uint32_t)(s.combo_count & 255) << 16) |
-           ((uint32_t)(s.line_count & 255) << 24);
-    w[2] = (uint32_t)(s.remaining & 0xFFFF) | ((uint32_t)(s.pending & 0xFFFF) << 16);
-    w[3] = (uint32_t)s.time_ms; w[4] = (uint32_t)s.combo_start; w[5] = (uint32_t)s.combo_time;
-    w[6] = (uint32_t)(s.drop_delay & 0xFFFF) | ((uint32_t)(s.incoming & 0xFFFF) << 16);
-    w[7] = (uint32_t)s.drop_delay_time; w[8] = (uint32_t)s.inc_dd_time; w[9] = (uint32_t)s.lockdown_time;
-    w[10] = (uint32_t)s.min_remaining; w[11] = s.piece_ctr;
-    w[12] = (uint32_t)(s.hole_ctr & 0xFFFF) | ((uint32_t)(s.hi12 & 0xFFFF) << 16);
-    w[13] = (uint32_t)(s.gq_n & 255) | ((uint32_t)(s.flags & 255) << 8);
+    PSWords u;
+    u.s = s;
+#pragma unroll
+    for (int i = 0; i < 14; i++) w[i] = u.w[i];
+    w[0] &= 0x03FFFFFFu; w[13] &= 0xFFFFu;      // padding bits are stored as zero
     w[23] = 0;   // words 14..22 (the garbage queue) never pass through registers
 }
 
@@ -420,8 +433,8 @@ B2T_HD bool dd_check(PS& s, int32_t t) {  // :3-21 (increaseDropDelay is the con
     if (t - s.drop_delay_time > s.drop_delay) { s.drop_delay_time = t; return true; }
     return false;
 }
-B2T_HD void dd_reset(PS& s, int32_t t) { s.drop_delay_time = t; s.lockdown = 0; }                  // :23-26
-B2T_HD void dd_set(PS& s, int32_t t) { if (!s.lockdown) s.lockdown_time = t + 400; s.lockdown = 1; }  // :37-41
+template <class ST> B2T_HD void dd_reset(ST& s, int32_t t) { s.drop_delay_time = t; s.lockdown = 0; }                  // :23-26
+template <class ST> B2T_HD void dd_set(ST& s, int32_t t) { if (!s.lockdown) s.lockdown_time = t + 400; s.lockdown = 1; }  // :37-41
 
 // ---- Garbage.cpp (queue front is index 0); S = stride of the queue words
 template <int S> B2T_HD int gq_count_at(const PS& s, int i) { return (int)(int16_t)(s.gq[(i >> 1) * S] >> (16 * (i & 1))); }
@@ -553,7 +566,7 @@ template <int S> B2T_HD int send_lines(PS& s, int lines) {
     return amount;
 }
 // gamePlay.cpp:48-52 hd_make
-template <class G, int S> B2T_HD void hd_make(PS& s, const Board<G, S>& b, const Tabs& tb) {
+template <class G, int S, class ST> B2T_HD void hd_make(ST& s, const Board<G, S>& b, const Tabs& tb) {
     if (s.kind > 6) return;
     const uint32_t pcc = pcc_of(tb, s.kind, s.rot);
     s.y = rest_from<G>(collide_mask<G, S>(b, s.x, pcc), s.y);
@@ -605,7 +618,7 @@ template <class G, int S> B2T_HD int delay_check(PS& s, const Board<G, S>& b, co
 
 // ---- keys (PythonHandle.cpp:73-112) and rotation with kicks (gameField.cpp:55-103)
 // pcn = column nibbles of the piece at its current rotation, kept in a register across keys
-template <class G, int S> B2T_HD void rotate_key(PS& s, const Board<G, S>& b, const Tabs& tb, int turn, uint32_t& pcn_cur) {
+template <class G, int S, class ST> B2T_HD void rotate_key(ST& s, const Board<G, S>& b, const Tabs& tb, int turn, uint32_t& pcn_cur) {
     const int nr = (s.rot + turn) & 3;
     const uint32_t pcn = pcn_of(tb, s.kind, nr);
     int x = s.x, y = s.y;
@@ -624,7 +637,7 @@ template <class G, int S> B2T_HD void rotate_key(PS& s, const Board<G, S>& b, co
 // `run` consecutive copies of one key (PythonHandle.cpp:73-112).  Repeats are folded where the outcome allows it: a lateral
 // step that is blocked stays blocked, n single downs are one descent of min(n, free rows) with the same DropDelay
 // bookkeeping (reset after any successful step, set after the first failed one; DropDelay.cpp:23-41 is idempotent).
-template <class G, int S> B2T_HD void apply_key_run(PS& s, const Board<G, S>& b, const Tabs& tb, int key, int run, uint32_t& pcn) {
+template <class G, int S, class ST> B2T_HD void apply_key_run(ST& s, const Board<G, S>& b, const Tabs& tb, int key, int run, uint32_t& pcn) {
     if (key >= 1 && key <= 4) {
         const int dx = (key & 1) ? key - 2 : key - 3;            // 1,2 -> -1 ; 3,4 -> +1
         const int steps = (key == 2 || key == 4) ? G::W : run;    // slam: until blocked
@@ -647,8 +660,8 @@ template <class G, int S> B2T_HD void apply_key_run(PS& s, const Board<G, S>& b,
 // The acting player's whole key string (4-bit tokens, word j at keys[j*KS]).  Every enumerated placement ends with the hard
 // drop; it is peeled off the loop so that all lanes of a warp lock their piece together instead of once per distinct length,
 // and the loop advances by runs of equal keys (the "n rows down" stretches of under-overhang placements are one step).
-template <class G, int S, int KS>
-B2T_HD void apply_keys(PS& s, const Board<G, S>& b, const Tabs& tb, const uint32_t* keys, int nkeys) {
+template <class G, int S, int KS, class ST>
+B2T_HD void apply_keys(ST& s, const Board<G, S>& b, const Tabs& tb, const uint32_t* keys, int nkeys) {
     if (s.kind > 6 || nkeys <= 0) return;
     uint32_t pcn = pcn_of(tb, s.kind, s.rot);
     const int last = nkeys - 1;

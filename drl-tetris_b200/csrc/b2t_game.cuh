@@ -13,7 +13,8 @@ template <class G, int S> struct Game {
     PS p[2];
     Board<G, S> b[2];
     uint32_t sc[2][SCALAR_WORDS];   // packed scalar words in flight between HBM and PS
-    B2T_HD int& gf() { return p[1].hi12; }            // game flags
+    B2T_HD int gf() const { return (int)p[1].hi12; }   // game flags
+    B2T_HD void set_gf(int v) { p[1].hi12 = (uint32_t)v & 0xFFFFu; }
     B2T_HD uint32_t seed16() const { return (uint32_t)p[0].hi12 & 0xFFFFu; }
 };
 
@@ -72,7 +73,7 @@ B2T_HD bool game_perform(Game<G, S>& g, const Tabs& tb, int player, const uint32
         // Only the fields a key can touch are moved into a neutral copy (selects, no dynamic register indexing);
         // the board is selected by pointer.
         const bool one = player != 0;
-        PS me;
+        Cur me;
         me.kind = one ? g.p[1].kind : g.p[0].kind;
         me.rot = one ? g.p[1].rot : g.p[0].rot;
         me.x = one ? g.p[1].x : g.p[0].x;
@@ -100,7 +101,7 @@ B2T_HD bool game_perform(Game<G, S>& g, const Tabs& tb, int player, const uint32
         const bool over = finish_actions<G, S>(g.p[0], g.b[0], g.p[1], g.b[1], tb, g.seed16(), elapsed, gf);
         gf = over ? (gf | GF_ENV_DONE) : (gf & ~GF_ENV_DONE);
     }
-    g.gf() = gf;
+    g.set_gf(gf);
     const bool done = (gf & GF_ENV_DONE) != 0;
     *reward = player ? reward_base(done, g.p[1].dead, g.p[0].dead) : reward_base(done, g.p[0].dead, g.p[1].dead);
     return done;
@@ -110,8 +111,8 @@ template <class G, int S> B2T_HD void game_reset(Game<G, S>& g, const Tabs& tb, 
     int gf = g.gf();
     const uint32_t s16 = seed & 0xFFFFu;
     reset_game<G, S>(g.p[0], g.b[0], g.p[1], g.b[1], tb, s16, gf);
-    g.p[0].hi12 = (int)s16;
-    g.p[1].hi12 = gf;   // round_over and env_done cleared (tetris_environment.py:66-68)
+    g.p[0].hi12 = s16;
+    g.p[1].hi12 = (uint32_t)gf & 0xFFFFu;   // round_over and env_done cleared (tetris_environment.py:66-68)
 }
 
 // Convert u8 keys (any value; >10 are no-ops like PythonHandle.cpp:109-110) to packed tokens
