@@ -134,7 +134,7 @@ int b2t_create(const b2t_config* cfg, b2t_handle** out) {
     CKC(cudaSetDevice(cfg->device));
     CKC(ops->prepare());
     const size_t n = (size_t)cfg->n_games;
-    h->state_vecs = (size_t)ops->NV * n;
+    h->state_vecs = (size_t)ops->NV * 32 * ((n + 31) / 32);   // tiles of 32 games
     CKC(cudaMalloc((void**)&h->state, h->state_vecs * sizeof(uint4)));
     CKC(cudaMalloc((void**)&h->kcache, n * sizeof(int32_t)));
     CKC(cudaMemset(h->kcache, 0, n * sizeof(int32_t)));
@@ -328,7 +328,7 @@ int b2t_export_state(b2t_handle* h, int32_t game, void* h_buf, void* stream) {
     if (!h || !h_buf || game < 0 || game >= h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_export_state: bad argument%s");
     CK(cudaSetDevice(h->cfg.device));
     cudaStream_t s = (cudaStream_t)stream;
-    gather_game_kernel<<<1, 64, 0, s>>>(h->state, h->cfg.n_games, game, h->ops->NV, h->xfer);
+    gather_game_kernel<<<1, 64, 0, s>>>(h->state, game, h->ops->NV, h->xfer);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h_buf, h->xfer, (size_t)h->ops->NV * 16, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -339,7 +339,7 @@ int b2t_import_state(b2t_handle* h, int32_t game, const void* h_buf, void* strea
     CK(cudaSetDevice(h->cfg.device));
     cudaStream_t s = (cudaStream_t)stream;
     CK(cudaMemcpyAsync(h->xfer, h_buf, (size_t)h->ops->NV * 16, cudaMemcpyHostToDevice, s));
-    scatter_game_kernel<<<1, 64, 0, s>>>(h->state, h->cfg.n_games, game, h->ops->NV, h->xfer);
+    scatter_game_kernel<<<1, 64, 0, s>>>(h->state, game, h->ops->NV, h->xfer);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
     return B2T_OK;

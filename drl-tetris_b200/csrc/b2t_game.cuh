@@ -1,13 +1,19 @@
 // b200tetris — one game = two players: HBM word layout, register/shared-memory working form, and the
 // perform_action body shared by the step and expand kernels (and by tests/hostsim on the CPU).
 //
-// HBM layout (struct-of-vectors so that thread g's loads coalesce): uint4 state[NV][n_games]; the 4*NV words
-// of game g are  [player0 | player1 | pad],  each player = W*CW column words, SW stream words, 24 scalars.
+// HBM layout: tiles of 32 games, struct-of-vectors inside a tile:  uint4 state[n_tiles][NV][32].  Thread g's loads
+// coalesce (a warp reads 512 contiguous bytes per vector) AND a warp's NV vectors are one contiguous NV*512-byte run, so a
+// step streams whole DRAM pages and touches one TLB entry per warp instead of NV.  The 4*NV words of game g are
+// [player0 | player1 | pad],  each player = W*CW column words, SW stream words, 24 scalars.
 #pragma once
 #include "b2t_core.cuh"
 #include "b2t_enum.cuh"
 
 namespace b2t {
+
+// index (in uint4 units) of vector v of game g
+template <class G> B2T_HD size_t state_index(int g, int v) { return ((size_t)(g >> 5) * G::NV + (size_t)v) * 32 + (size_t)(g & 31); }
+template <class G> B2T_HD size_t state_vectors(int n_games) { return (size_t)((n_games + 31) >> 5) * G::NV * 32; }
 
 template <class G, int S> struct Game {
     PS p[2];

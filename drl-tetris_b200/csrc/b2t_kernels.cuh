@@ -320,10 +320,10 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
         int kc = 0;
         if (by_cache) kc = p.kcache[gi];
         {
-            const uint4* src = p.state + gi;
+            const uint4* src = p.state + state_index<G>(gi, 0);
 #pragma unroll
             for (int v = 0; v < G::NV; v++) {
-                const uint4 q = src[(size_t)v * (size_t)p.n_games];
+                const uint4 q = src[v * 32];
                 game_put_word(g, 4 * v + 0, q.x);
                 game_put_word(g, 4 * v + 1, q.y);
                 game_put_word(g, 4 * v + 2, q.z);
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
         st_rng = ((flags_after & ~flags_before) & 2) != 0;
         if ((p.flags & KF_STORE) && !expand) {
             game_pack(g);
-            uint4* dst = p.state + gi;
+            uint4* dst = p.state + state_index<G>(gi, 0);
 #pragma unroll
             for (int v = 0; v < G::NV; v++) {
                 uint4 q;
@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
                 q.y = game_get_word(g, 4 * v + 1);
                 q.z = game_get_word(g, 4 * v + 2);
                 q.w = game_get_word(g, 4 * v + 3);
-                dst[(size_t)v * (size_t)p.n_games] = q;
+                dst[v * 32] = q;
             }
         }
         if (p.piece_idx) {
@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
         gi = p.idx ? p.idx[i] : i;
         const int pl = p.player[i] ? 1 : 0;
         const uint32_t* words = reinterpret_cast<const uint32_t*>(p.state);
-        auto word = [&](int wi) { return words[((size_t)(wi >> 2) * (size_t)p.n_games + (size_t)gi) * 4 + (wi & 3)]; };
+        auto word = [&](int wi) { return words[state_index<G>(gi, wi >> 2) * 4 + (wi & 3)]; };
         const int base = pl * G::PW;
         for (int c = 0; c < G::W; c++) {
             if (G::CW == 1) b.col(c) = (col_t)word(base + c);
@@ -903,19 +903,19 @@ __global__ void __launch_bounds__(TPB) init_kernel(uint4* state, int n_games) {
         uint4 q;
         q.x = game_get_word(g, 4 * v + 0); q.y = game_get_word(g, 4 * v + 1);
         q.z = game_get_word(g, 4 * v + 2); q.w = game_get_word(g, 4 * v + 3);
-        state[(size_t)v * (size_t)n_games + gi] = q;
+        state[state_index<G>(gi, v)] = q;
     }
 }
 
 #ifdef B2T_COMMON_KERNELS
 // export/import one game's NV vectors <-> contiguous buffer
-__global__ void gather_game_kernel(const uint4* state, int n_games, int game, int nv, uint4* out) {
+__global__ void gather_game_kernel(const uint4* state, int game, int nv, uint4* out) {      // tile layout, see b2t_game.cuh
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v < nv) out[v] = state[(size_t)v * n_games + game];
+    if (v < nv) out[v] = state[((size_t)(game >> 5) * nv + v) * 32 + (game & 31)];
 }
-__global__ void scatter_game_kernel(uint4* state, int n_games, int game, int nv, const uint4* in) {
+__global__ void scatter_game_kernel(uint4* state, int game, int nv, const uint4* in) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v < nv) state[(size_t)v * n_games + game] = in[v];
+    if (v < nv) state[((size_t)(game >> 5) * nv + v) * 32 + (game & 31)] = in[v];
 }
 
 #endif  // B2T_COMMON_KERNELS

@@ -83,7 +83,7 @@ template <int H, int W> struct HS : HSBase {
         tb.pcn = pt.pcn; tb.pcc = pt.pcc; tb.piece = piece_tab.data(); tb.hole = hole_tab.data(); tb.powtab = powtab;
         tb.piece_len = piece_len; tb.hole_len = hole_len; tb.spawn_rots = 0;
         for (int k = 0; k < 7; k++) tb.spawn_rots |= (uint32_t)pt.spawn_rot[k] << (2 * k);
-        state.assign((size_t)G::NV * 4 * n, 0);
+        state.assign(state_vectors<G>(n) * 4, 0);
         Game<G, 1> g;
         bind(g);
         for (int i = 0; i < n; i++) { game_init(g); save(g, i); }
@@ -102,13 +102,13 @@ template <int H, int W> struct HS : HSBase {
     }
     void load(Game<G, 1>& g, int gi) {
         for (int v = 0; v < G::NV; v++)
-            for (int k = 0; k < 4; k++) game_put_word(g, 4 * v + k, state[((size_t)v * n + gi) * 4 + k]);
+            for (int k = 0; k < 4; k++) game_put_word(g, 4 * v + k, state[state_index<G>(gi, v) * 4 + k]);
         game_unpack(g);
     }
     void save(Game<G, 1>& g, int gi) {
         game_pack(g);
         for (int v = 0; v < G::NV; v++)
-            for (int k = 0; k < 4; k++) state[((size_t)v * n + gi) * 4 + k] = game_get_word(g, 4 * v + k);
+            for (int k = 0; k < 4; k++) state[state_index<G>(gi, v) * 4 + k] = game_get_word(g, 4 * v + k);
     }
     void reset(const int32_t* idx, int cnt, const uint32_t* seeds) override {
         Game<G, 1> g; bind(g);
