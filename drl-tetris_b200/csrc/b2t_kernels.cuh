@@ -12,10 +12,13 @@
 
 namespace b2t {
 
-#ifndef B2T_GAME_MINB
-#define B2T_GAME_MINB 4   // resident blocks per SM the step/expand kernel is register-capped for
+#ifndef B2T_TPB
+#define B2T_TPB 128
 #endif
-constexpr int TPB = 128;
+#ifndef B2T_GAME_MINB
+#define B2T_GAME_MINB (512 / B2T_TPB)   // resident blocks per SM the step/expand kernel is register-capped for (16 warps)
+#endif
+constexpr int TPB = B2T_TPB;
 constexpr int WARPS = TPB / 32;
 constexpr int STAT_SLICES = 64;
 constexpr int STAT_WORDS = 8;
