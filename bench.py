@@ -201,6 +201,8 @@ def main():
     ap.add_argument("--boards", type=int, default=1 << 16, help="boards per GPU for the world-model leg")
     ap.add_argument("--no-extras", action="store_true", help="skip placements / e2e / cpu legs (profiling runs)")
     ap.add_argument("--leg", default="all", help="all | step | placements  (profiling runs: time only one leg)")
+    ap.add_argument("--cuda-profile", default="", help="step | placements: bracket ONE extra untimed iteration of that leg with "
+                    "cudaProfilerStart/Stop after its timed region (for `ncu --profile-from-start off`)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -266,6 +268,8 @@ def main():
         ev[t + 1].record()
     torch.cuda.synchronize()
     wall1 = time.perf_counter()
+    if a.cuda_profile == "step":
+        torch.cuda.profiler.start(); one_step(a.warmup + a.steps); torch.cuda.synchronize(); torch.cuda.profiler.stop()
     total_ms = ev[0].elapsed_time(ev[-1])
     per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.steps)]
     clocks = sampler.summary(wall0, wall1)
@@ -385,6 +389,8 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
+        if a.cuda_profile == "placements":
+            torch.cuda.profiler.start(); expand(); torch.cuda.synchronize(); torch.cuda.profiler.stop()
         pt = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(pt, op=dist.ReduceOp.MAX)

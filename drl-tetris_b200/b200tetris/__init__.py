@@ -4,3 +4,4 @@ from ._lib import B2TError, LIB_PATH, VEC_LEN, load  # noqa: F401
 from .engine import Engine, piece_map  # noqa: F401
 from .vector_env import action, action_list, null_action, state, tetris_environment_vector  # noqa: F401
 from . import sharding  # noqa: F401
+from . import tetris_env  # noqa: F401  (per-env facade: the reference's pybind11 module surface)

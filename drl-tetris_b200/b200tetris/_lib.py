@@ -43,6 +43,19 @@ class ExpandArgs(C.Structure):
                 ("lmax", C.c_int32), ("d_reward", vp), ("d_done", vp), ("d_lines", vp), ("obs", Obs)]
 
 
+class PlayerRaw(C.Structure):   # b2t_player_raw
+    _fields_ = [("piece", C.c_uint8 * 16)] + [(k, C.c_int32) for k in (
+        "x", "y", "inc_lines", "combo_time", "combo_count", "nextpiece", "reward", "dead", "piece_kind", "rotation", "time_ms",
+        "drop_delay", "drop_delay_time", "increase_drop_delay_time", "lockdown_time", "lockdown", "combo_start", "combo_time_total",
+        "line_count", "min_remaining", "incoming_lines", "lines_pending", "garbage_n")] + [
+        ("garbage_count", C.c_int32 * 6), ("garbage_delay", C.c_int32 * 6), ("piece_draws", C.c_int32), ("hole_draws", C.c_int32)]
+
+
+class GameRaw(C.Structure):     # b2t_game_raw
+    _fields_ = [("seed16", C.c_int32), ("round_over", C.c_int32), ("done", C.c_int32), ("last_winner", C.c_int32),
+                ("overflow", C.c_int32), ("player", PlayerRaw * 2)]
+
+
 SYMBOLS = {
     "b2t_create": (C.c_int, [C.POINTER(Config), C.POINTER(vp)]),
     "b2t_destroy": (C.c_int, [vp]),
@@ -58,6 +71,9 @@ SYMBOLS = {
     "b2t_restore": (C.c_int, [vp, C.c_int32, vp]),
     "b2t_export_state": (C.c_int, [vp, C.c_int32, vp, vp]),
     "b2t_import_state": (C.c_int, [vp, C.c_int32, vp, vp]),
+    "b2t_get_game": (C.c_int, [vp, C.c_int32, C.POINTER(GameRaw), u8p]),
+    "b2t_set_game": (C.c_int, [vp, C.c_int32, C.POINTER(GameRaw), u8p]),
+    "b2t_copy_game": (C.c_int, [vp, C.c_int32, vp, C.c_int32, vp]),
     "b2t_poke_dead": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, vp]),
     "b2t_clear_field": (C.c_int, [vp, C.c_int32, C.c_int32, vp]),
     "b2t_stats": (C.c_int, [vp, u64p, vp]),

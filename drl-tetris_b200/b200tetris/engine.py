@@ -175,6 +175,22 @@ class Engine:
         assert buf.size == self.state_bytes
         self._ck(self.lib.b2t_import_state(self._h, int(game), buf.ctypes.data_as(C.c_void_p), None))
 
+    def get_game(self, game, want_field=True):
+        """b2t_get_game: (GameRaw, field u8[2,H,W] or None) — the game in the reference's own terms"""
+        raw = _lib.GameRaw()
+        field = np.empty((2, self.H, self.W), np.uint8) if want_field else None
+        self._ck(self.lib.b2t_get_game(self._h, int(game), C.byref(raw), _hp(field, C.c_uint8)))
+        return raw, field
+
+    def set_game(self, game, raw, field=None):
+        field = None if field is None else np.ascontiguousarray(field, np.uint8)
+        assert field is None or field.shape == (2, self.H, self.W)
+        self._ck(self.lib.b2t_set_game(self._h, int(game), C.byref(raw), _hp(field, C.c_uint8)))
+
+    def copy_game(self, dst, src_engine, src):
+        """PythonHandle.copy()/set() of one game slot (device-side, possibly from another handle of the same field size)"""
+        self._ck(self.lib.b2t_copy_game(self._h, int(dst), src_engine._h, int(src), None))
+
     def poke_dead(self, game, player, dead):
         self._ck(self.lib.b2t_poke_dead(self._h, int(game), int(player), int(bool(dead)), None))
 

@@ -345,6 +345,35 @@ int b2t_import_state(b2t_handle* h, int32_t game, const void* h_buf, void* strea
     return B2T_OK;
 }
 
+int b2t_get_game(b2t_handle* h, int32_t game, b2t_game_raw* out, uint8_t* h_field) {
+    if (!h || !out || game < 0 || game >= h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_get_game: bad argument%s");
+    std::vector<uint32_t> words((size_t)h->ops->NV * 4);
+    if (int r = b2t_export_state(h, game, words.data(), nullptr)) return r;
+    h->ops->decode(words.data(), out, h_field);
+    return B2T_OK;
+}
+int b2t_set_game(b2t_handle* h, int32_t game, const b2t_game_raw* in, const uint8_t* h_field) {
+    if (!h || !in || game < 0 || game >= h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_set_game: bad argument%s");
+    for (int p = 0; p < 2; p++)
+        if (in->player[p].piece_kind < 0 || in->player[p].piece_kind > 7 || in->player[p].nextpiece < 0 || in->player[p].nextpiece > 7)
+            return fail(h, B2T_ERR_ARG, "b2t_set_game: piece_kind / nextpiece out of range%s");
+    std::vector<uint32_t> words((size_t)h->ops->NV * 4);
+    if (int r = b2t_export_state(h, game, words.data(), nullptr)) return r;
+    h->ops->encode(words.data(), in, h_field);
+    return b2t_import_state(h, game, words.data(), nullptr);
+}
+int b2t_copy_game(b2t_handle* to, int32_t dst, b2t_handle* from, int32_t src, void* stream) {
+    b2t_handle* h = to;
+    if (!to || !from || dst < 0 || dst >= to->cfg.n_games || src < 0 || src >= from->cfg.n_games)
+        return fail(h, B2T_ERR_ARG, "b2t_copy_game: bad argument%s");
+    if (to->ops != from->ops || to->cfg.device != from->cfg.device)
+        return fail(h, B2T_ERR_ARG, "b2t_copy_game: handles differ in field size or device%s");
+    CK(cudaSetDevice(h->cfg.device));
+    copy_game_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(to->state, dst, from->state, src, h->ops->NV);
+    CK(cudaGetLastError());
+    return B2T_OK;
+}
+
 static int poke(b2t_handle* h, int32_t game, int32_t player, uint32_t flag, int value, void* stream) {
     if (!h || game < 0 || game >= h->cfg.n_games || player < 0 || player > 1) return fail(h, B2T_ERR_ARG, "poke: bad game/player%s");
     CK(cudaSetDevice(h->cfg.device));

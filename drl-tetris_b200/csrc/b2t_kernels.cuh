@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include "b2t_game.cuh"
+#include "b2t_raw.cuh"
 #include "b2t_rng.cuh"
 
 namespace b2t {
@@ -256,7 +257,10 @@ __device__ __forceinline__ uint32_t spread_nibbles(uint32_t x) {
 }
 
 // ---------------------------------------------------------------------------------------------- the game kernel
-template <class G>
+// MODE: 0 = every flag is read at run time (reset / observe / pokes / steps without write-back);  1 = expand and 2 = the plain
+// stored step are compiled with their flag set fixed, so the two hot variants carry no code for the others' paths.
+constexpr int GM_GENERIC = 0, GM_EXPAND = 1, GM_STEP = 2;
+template <class G, int MODE>
 __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams p) {
     typedef typename G::col_t col_t;
     typedef SmemLayout<G> L;
@@ -272,6 +276,13 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
     uint8_t* s_vec = wbase + L::BITS;
     uint16_t* s_tab = reinterpret_cast<uint16_t*>(smem + WARPS * L::WARP_BYTES);
     const int row = blockIdx.x * TPB + tid;
+    const uint32_t flags = MODE == GM_EXPAND ? (KF_EXPAND | (p.flags & KF_FINALIZE))
+                         : MODE == GM_STEP ? (KF_STEP | KF_STORE | (p.flags & KF_FINALIZE)) : p.flags;
+    if (MODE == GM_EXPAND) {   // the grid covers the caller's capacity; blocks past the actual row count leave at once
+        int t = p.offsets[p.n];
+        if (t > p.capacity) t = p.capacity;
+        if (blockIdx.x * TPB >= t) return;
+    }
     if (tid < 28) { s_tab[tid] = p.tabs.pcn[tid]; s_tab[32 + tid] = p.tabs.pcc[tid]; }
     Tabs tb;
     tb.pcn = s_tab; tb.pcc = s_tab + 32;
@@ -288,8 +299,8 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
     }
     __syncthreads();
 
-    const bool expand = (p.flags & KF_EXPAND) != 0;
-    const bool stepping = (p.flags & (KF_STEP | KF_EXPAND)) != 0;
+    const bool expand = (flags & KF_EXPAND) != 0;
+    const bool stepping = (flags & (KF_STEP | KF_EXPAND)) != 0;
     int total_rows = p.n, i = row, k = 0;
     if (expand) {
         total_rows = p.offsets[p.n];
@@ -335,11 +346,11 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
         }
         game_unpack(g);
         const int flags_before = g.p[0].flags | g.p[1].flags;
-        if (p.flags & KF_RESET) game_reset(g, tb, p.seeds[i]);
-        if (p.flags & KF_POKE_DEAD) {
+        if (flags & KF_RESET) game_reset(g, tb, p.seeds[i]);
+        if (flags & KF_POKE_DEAD) {
             if (p.poke_player == 0) g.p[0].dead = p.poke_value; else g.p[1].dead = p.poke_value;
         }
-        if (p.flags & KF_CLEAR_FIELD) {
+        if (flags & KF_CLEAR_FIELD) {
             if (p.poke_player == 0) board_clear<G, WS>(g.b[0]); else board_clear<G, WS>(g.b[1]);
         }
         if (stepping) {
@@ -385,7 +396,7 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
                 }
             }
             const bool was_over = (g.gf() & GF_ROUND_OVER) != 0;
-            const bool finalize = (p.flags & KF_FINALIZE) != 0;
+            const bool finalize = (flags & KF_FINALIZE) != 0;
             int rew;
             const bool done = game_perform<G, WS, WS>(g, tb, player, kw, nkeys, finalize, p.elapsed, &rew);
             if (p.reward) p.reward[row] = (int8_t)rew;
@@ -429,7 +440,7 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
         const int flags_after = g.p[0].flags | g.p[1].flags;
         st_gq = ((flags_after & ~flags_before) & 1) != 0;
         st_rng = ((flags_after & ~flags_before) & 2) != 0;
-        if ((p.flags & KF_STORE) && !expand) {
+        if ((flags & KF_STORE) && !expand) {
             game_pack(g);
             uint4* dst = p.state + state_index<G>(gi, 0);
 #pragma unroll
@@ -469,7 +480,7 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
     if (p.vec && valid_rows > 0)
         emit_vecs(s_vec, g.p[0], g.p[1], swap, active, p.vec + (size_t)warp_row0 * (size_t)(2 * VEC_LEN), valid_rows, lane);
     // ---- episode statistics: one atomic per non-zero counter per warp, spread over slices
-    if (p.stats && (p.flags & KF_STEP)) {
+    if (p.stats && (flags & KF_STEP)) {
         int vals[STAT_WORDS] = {st_steps, st_done, st_w0, st_w1, st_both, st_lines, st_gq, st_rng};
 #pragma unroll
         for (int j = 0; j < STAT_WORDS; j++) {
@@ -845,18 +856,29 @@ __global__ void __launch_bounds__(256) select_kernel(const float* scores, const 
     }
     placement[i] = best;
 }
-// row -> {board slot, game id, placement, player} for expand: one thread per board writes its K consecutive rows
+// row -> {board slot, game id, placement, player} for expand: a block takes 256 consecutive boards, its threads walk the rows
+// of those boards in order (coalesced 16-byte stores) and find each row's board by bisection of the offsets in shared memory
 __global__ void __launch_bounds__(256) fill_row_meta(const int32_t* offsets, int n, const int32_t* idx, const uint8_t* player,
                                                      int4* row_meta, int32_t* row_board, int capacity) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int a = offsets[i];
-    int b = offsets[i + 1];
-    if (b > capacity) b = capacity;
-    const int gi = idx ? idx[i] : i, pl = player[i] ? 1 : 0;
-    for (int r = a; r < b; r++) {
-        row_meta[r] = make_int4(i, gi, r - a, pl);
-        if (row_board) row_board[r] = i;
+    __shared__ int s_off[257];
+    __shared__ int s_gi[256];
+    __shared__ uint8_t s_pl[256];
+    const int b0 = blockIdx.x * 256, tid = threadIdx.x;
+    const int nb = (n - b0) < 256 ? (n - b0) : 256;
+    for (int t = tid; t <= nb; t += 256) s_off[t] = offsets[b0 + t];
+    if (tid < nb) { s_gi[tid] = idx ? idx[b0 + tid] : b0 + tid; s_pl[tid] = player[b0 + tid] ? 1 : 0; }
+    __syncthreads();
+    const int r0 = s_off[0];
+    int r1 = s_off[nb];
+    if (r1 > capacity) r1 = capacity;
+    for (int r = r0 + tid; r < r1; r += 256) {
+        int lo = 0, hi = nb;              // s_off[lo] <= r < s_off[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_off[mid] <= r) lo = mid; else hi = mid;
+        }
+        row_meta[r] = make_int4(b0 + lo, s_gi[lo], r - s_off[lo], (int)s_pl[lo]);
+        if (row_board) row_board[r] = b0 + lo;
     }
 }
 __global__ void __launch_bounds__(SCAN_TPB) scan_finish(const int32_t* K, int n, const int32_t* sums, int32_t* offsets) {
@@ -920,6 +942,11 @@ __global__ void scatter_game_kernel(uint4* state, int game, int nv, const uint4*
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v < nv) state[((size_t)(game >> 5) * nv + v) * 32 + (game & 31)] = in[v];
 }
+// PythonHandle.copy()/set() of one game, possibly between two handles of the same field size
+__global__ void copy_game_kernel(uint4* dst_state, int dst, const uint4* src_state, int src, int nv) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < nv) dst_state[((size_t)(dst >> 5) * nv + v) * 32 + (dst & 31)] = src_state[((size_t)(src >> 5) * nv + v) * 32 + (src & 31)];
+}
 
 #endif  // B2T_COMMON_KERNELS
 
@@ -931,12 +958,18 @@ struct GeomOps {
     cudaError_t (*launch_enum)(const EParams&, cudaStream_t);
     cudaError_t (*launch_unpack)(const uint32_t*, const int32_t*, const int32_t*, int, int, int, uint8_t*, uint8_t*, cudaStream_t);
     cudaError_t (*launch_init)(uint4*, int, cudaStream_t);
+    void (*decode)(const uint32_t* words, b2t_game_raw* out, uint8_t* field);          // host codec, b2t_raw.cuh
+    void (*encode)(uint32_t* words, const b2t_game_raw* in, const uint8_t* field);
 };
 
 template <class G> struct Launch {
     typedef SmemLayout<G> L;
     static cudaError_t prepare() {
-        cudaError_t e = cudaFuncSetAttribute(game_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::GAME_TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(game_kernel<G, GM_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::GAME_TOTAL);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(game_kernel<G, GM_EXPAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::GAME_TOTAL);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(game_kernel<G, GM_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::GAME_TOTAL);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(enumerate_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, EnumCfg<G>::SMEM);
         if (e != cudaSuccess) return e;
@@ -944,7 +977,10 @@ template <class G> struct Launch {
     }
     static cudaError_t game(const KParams& p, int rows, cudaStream_t s) {
         if (rows <= 0) return cudaSuccess;
-        game_kernel<G><<<(rows + TPB - 1) / TPB, TPB, L::GAME_TOTAL, s>>>(p);
+        const dim3 grid((rows + TPB - 1) / TPB);
+        if ((p.flags & ~KF_FINALIZE) == KF_EXPAND) game_kernel<G, GM_EXPAND><<<grid, TPB, L::GAME_TOTAL, s>>>(p);
+        else if ((p.flags & ~KF_FINALIZE) == (KF_STEP | KF_STORE)) game_kernel<G, GM_STEP><<<grid, TPB, L::GAME_TOTAL, s>>>(p);
+        else game_kernel<G, GM_GENERIC><<<grid, TPB, L::GAME_TOTAL, s>>>(p);
         return cudaGetLastError();
     }
     static cudaError_t enumerate(const EParams& p, cudaStream_t s) {
@@ -965,7 +1001,7 @@ template <class G> struct Launch {
     }
     static const GeomOps* ops() {
         static const GeomOps o = {G::H, G::W, G::NV, G::KMAX, G::KEYW, G::LMAX, L::GAME_TOTAL, EnumCfg<G>::SMEM,
-                                  &prepare, &game, &enumerate, &unpack, &init};
+                                  &prepare, &game, &enumerate, &unpack, &init, &decode_game<G>, &encode_game<G>};
         return &o;
     }
 };

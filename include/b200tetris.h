@@ -158,6 +158,51 @@ int b2t_restore(b2t_handle *h, int32_t slot, void *stream);
 int b2t_export_state(b2t_handle *h, int32_t game, void *h_buf, void *stream);
 int b2t_import_state(b2t_handle *h, int32_t game, const void *h_buf, void *stream);
 
+/* ---- one game in the reference's own terms: what PythonHandle.states[p] shows (PythonHandle.h:54-82) plus the hidden
+ * members its pickle support walks (PythonHandle.h:207-308).  This is the exchange format of the per-env compatibility
+ * facade (b200tetris/tetris_env.py: a PythonHandle-shaped object per game slot), of pickling, and of white-box tests. */
+typedef struct {
+    /* State views */
+    uint8_t piece[16];          /* field.piece.grid: 4x4, colour code of the piece (1..7, state_processors.py:24) or 0 */
+    int32_t x, y;               /* field.piece.posX/posY */
+    int32_t inc_lines;          /* incoming_lines_count */
+    int32_t combo_time;         /* combo.remaining (uint16) */
+    int32_t combo_count;        /* combo.comboCount */
+    int32_t nextpiece;
+    int32_t reward;             /* lines cleared by the last finish_action */
+    int32_t dead;
+    /* hidden */
+    int32_t piece_kind;         /* field.piece.piece 0..6; 7 = no piece yet (never-reset game) */
+    int32_t rotation;           /* field.piece.current_rotation */
+    int32_t time_ms;            /* GamePlay::time_ms */
+    int32_t drop_delay, drop_delay_time, increase_drop_delay_time, lockdown_time, lockdown;   /* DropDelay.h:6-18 */
+    int32_t combo_start, combo_time_total, line_count;                                        /* Combo.h:8-33 comboStart, comboTime, lineCount */
+    int32_t min_remaining;      /* GarbageHandler::minRemaining */
+    int32_t incoming_lines;     /* GamePlay::incoming_lines (float in the reference; integral with two players) */
+    int32_t lines_pending;      /* data.linesCleared - linesCleared */
+    int32_t garbage_n;          /* GarbageHandler::garbage.size() (at most 6 are kept) */
+    int32_t garbage_count[6];
+    int32_t garbage_delay[6];
+    int32_t piece_draws, hole_draws;   /* position in the player's piece / hole stream (rander) */
+} b2t_player_raw;
+
+typedef struct {
+    int32_t seed16;             /* the (short) seed of the current round (randomizer.cpp:34-36,47-49) */
+    int32_t round_over;         /* PythonHandle::round_over */
+    int32_t done;               /* tetris_environment.done as maintained by b2t_step */
+    int32_t last_winner;        /* PythonHandle::last_winner */
+    int32_t overflow;           /* bit 0: garbage queue outgrew 6 entries, bit 1: a stream table was outrun */
+    b2t_player_raw player[2];
+} b2t_game_raw;
+
+/* h_field: optional [2, H, W] bytes, the players' fields (non-zero = occupied).  b2t_set_game with h_field == NULL keeps the
+ * boards.  `piece` is output only (the piece is set through piece_kind / rotation).  Both synchronise. */
+int b2t_get_game(b2t_handle *h, int32_t game, b2t_game_raw *out, uint8_t *h_field);
+int b2t_set_game(b2t_handle *h, int32_t game, const b2t_game_raw *in, const uint8_t *h_field);
+/* PythonHandle.copy() / set() for single games: game `src` of handle `from` into game `dst` of handle `to` (same field size,
+ * same device; `from` may be `to`).  Asynchronous on `stream`. */
+int b2t_copy_game(b2t_handle *to, int32_t dst, b2t_handle *from, int32_t src, void *stream);
+
 /* The writable numpy views the front-end pokes (data_types/state.py:9-17 dead[0]=1; scripts/eval.py:156 field[:,:]=0) */
 int b2t_poke_dead(b2t_handle *h, int32_t game, int32_t player, int32_t dead, void *stream);
 int b2t_clear_field(b2t_handle *h, int32_t game, int32_t player, void *stream);

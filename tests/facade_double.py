@@ -1,0 +1,60 @@
+"""TEST INFRASTRUCTURE ONLY.  A CPU stand-in for b200tetris.Engine with the handful of methods the per-env facade
+(b200tetris/tetris_env.py) calls, backed by tests/hostsim (the engine's own game-core headers compiled for the CPU).  It lets the
+GPU-less container run the facade's Python — and, where /root/reference is present, the reference's unmodified front-end on
+top of it — against the compiled reference.  The product never sees it: b200tetris.tetris_env defaults to the CUDA Engine, and
+the `-m gpu` tests run the same cases on the real engine."""
+import numpy as np
+
+import harness  # noqa: F401
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
+import pyhostsim  # noqa: E402
+
+
+class HostSimEngine:
+    def __init__(self, n_games, height, width, pieces, n_players=2, bar_null_moves=True, time_ms_per_action=400, device=0):
+        assert n_players == 2 and bar_null_moves
+        self.v = pyhostsim.HostSimVector(n_games, height, width, pieces)
+        self.n, self.H, self.W = n_games, height, width
+        self.kmax, self.lmax = (256, 128) if width > 10 else (96, 64)
+        self.default_ms = time_ms_per_action
+        self._h = self.v.h
+
+    def reset(self, seeds, idx=None):
+        self.v.reset(seeds, idx)
+
+    def step(self, player, keys, key_len, idx=None, time_ms=0, finalize=True, **_):
+        return self.v.step(player, keys, key_len, idx, time_ms=time_ms if time_ms > 0 else self.default_ms, finalize=finalize)
+
+    def enumerate(self, player, idx=None, kmax=None, lmax=None, want_keys=True):
+        K, keys, klen, _, bad = self.v.enumerate(player, idx, True, kmax or self.kmax, lmax or self.lmax)
+        assert bad == 0
+        return K, keys, klen
+
+    def get_game(self, game, want_field=True):
+        return self.v.get_game(game, want_field)
+
+    def set_game(self, game, raw, field=None):
+        self.v.set_game(game, raw, field)
+
+    def copy_game(self, dst, src_engine, src):
+        self.v.copy_game(dst, src_engine.v, src)
+
+
+def install():
+    """Point the facade at the CPU double; returns the facade module with small arenas."""
+    from b200tetris import tetris_env
+    tetris_env._engine_factory = HostSimEngine
+    tetris_env._arenas.clear()
+    tetris_env.set_arena_slots(64)
+    return tetris_env
+
+
+def uninstall():
+    from b200tetris import tetris_env
+    from b200tetris.engine import Engine
+    tetris_env._engine_factory = Engine
+    tetris_env._arenas.clear()
+    tetris_env.set_arena_slots(4096)

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "b2t_game.cuh"
+#include "b2t_raw.cuh"
 #include "b2t_geoms.h"
 #include "b2t_rng.cuh"
 
@@ -30,6 +31,11 @@ struct HSBase {
                        int32_t* K, uint8_t* keys, uint8_t* key_len, uint8_t* field, uint8_t* vec, uint8_t* pidx, int8_t* reward,
                        uint8_t* done, uint8_t* lines) = 0;
     virtual int flags(int game) = 0;
+    virtual void get_game(int game, b2t_game_raw* out, uint8_t* field) = 0;
+    virtual void set_game(int game, const b2t_game_raw* in, const uint8_t* field) = 0;
+    virtual void copy_game(int dst, HSBase* from, int src) = 0;
+    virtual void words_of(int game, uint32_t* out) = 0;
+    virtual int nwords() = 0;
 };
 
 template <int KW> struct ListSink {
@@ -238,6 +244,38 @@ template <int H, int W> struct HS : HSBase {
         }
         return nbad;
     }
+    int nwords() override { return 4 * G::NV; }
+    void words_of(int gi, uint32_t* out) override {
+        for (int v = 0; v < G::NV; v++)
+            for (int k = 0; k < 4; k++) out[4 * v + k] = state[state_index<G>(gi, v) * 4 + k];
+    }
+    void put_words(int gi, const uint32_t* in) {
+        for (int v = 0; v < G::NV; v++)
+            for (int k = 0; k < 4; k++) state[state_index<G>(gi, v) * 4 + k] = in[4 * v + k];
+    }
+    void get_game(int gi, b2t_game_raw* out, uint8_t* field) override {   // the product's host codec (b2t_raw.cuh) on this store
+        uint32_t w[4 * G::NV];
+        words_of(gi, w);
+        decode_game<G>(w, out, field);
+    }
+    void set_game(int gi, const b2t_game_raw* in, const uint8_t* field) override {
+        uint32_t w[4 * G::NV];
+        words_of(gi, w);
+        encode_game<G>(w, in, field);
+        put_words(gi, w);
+        ensure_row((uint32_t)in->seed16 & 0xFFFF);
+    }
+    void copy_game(int dst, HSBase* from, int src) override {
+        uint32_t w[4 * G::NV];
+        from->words_of(src, w);
+        put_words(dst, w);
+        ensure_row(seed_of(w));
+    }
+    uint32_t seed_of(const uint32_t* w) {
+        b2t_game_raw r;
+        decode_game<G>(w, &r, nullptr);
+        return (uint32_t)r.seed16 & 0xFFFF;
+    }
     int flags(int gi) override {
         Game<G, 1> g; bind(g);
         load(g, gi);
@@ -270,4 +308,7 @@ int hs_expand(void* h, const int32_t* idx, int n, const uint8_t* player, int bar
     return ((HSBase*)h)->expand(idx, n, player, bar_null, finalize, time_ms, kmax, lmax, K, keys, key_len, field, vec, pidx, reward, done, lines);
 }
 int hs_flags(void* h, int game) { return ((HSBase*)h)->flags(game); }
+void hs_get_game(void* h, int game, b2t_game_raw* out, uint8_t* field) { ((HSBase*)h)->get_game(game, out, field); }
+void hs_set_game(void* h, int game, const b2t_game_raw* in, const uint8_t* field) { ((HSBase*)h)->set_game(game, in, field); }
+void hs_copy_game(void* to, int dst, void* from, int src) { ((HSBase*)to)->copy_game(dst, (HSBase*)from, src); }
 }

@@ -17,7 +17,7 @@ def build(force=False):
     if not force and os.path.exists(_LIB) and all(os.path.getmtime(_LIB) > os.path.getmtime(s) for s in srcs):
         return
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas",
-                           "-I" + _SRC, "-x", "c++", os.path.join(_HERE, "hostsim.cpp"), "-o", _LIB])
+                           "-I" + _SRC, "-I" + os.path.join(_HERE, "..", "..", "include"), "-x", "c++", os.path.join(_HERE, "hostsim.cpp"), "-o", _LIB])
 
 
 def lib():
@@ -37,6 +37,9 @@ def lib():
         L.hs_enumerate.argtypes = [vp, i32p, i32, u8p, i32, i32, i32, i32p, u8p, u8p]
         L.hs_expand.restype = i32
         L.hs_expand.argtypes = [vp, i32p, i32, u8p, i32, i32, i32, i32, i32, i32p, u8p, u8p, u8p, u8p, u8p, i8p, u8p, u8p]
+        L.hs_get_game.argtypes = [vp, i32, vp, u8p]
+        L.hs_set_game.argtypes = [vp, i32, vp, u8p]
+        L.hs_copy_game.argtypes = [vp, i32, vp, i32]
         L.hs_flags.restype = i32
         L.hs_flags.argtypes = [vp, i32]
         _lib = L
@@ -112,6 +115,20 @@ class HostSimVector:
                                    _p(o["vec"], C.c_uint8), _p(o["piece_idx"], C.c_uint8), _p(o["reward"], C.c_int8), _p(o["done"], C.c_uint8),
                                    _p(o["lines"], C.c_uint8))
         return o
+
+    def get_game(self, game, want_field=True):
+        from b200tetris import _lib as abi   # struct layout only (ctypes mirror of b2t_game_raw)
+        raw = abi.GameRaw()
+        field = np.zeros((2, self.H, self.W), np.uint8) if want_field else None
+        lib().hs_get_game(self.h, int(game), C.byref(raw), _p(field, C.c_uint8))
+        return raw, field
+
+    def set_game(self, game, raw, field=None):
+        field = None if field is None else np.ascontiguousarray(field, np.uint8)
+        lib().hs_set_game(self.h, int(game), C.byref(raw), _p(field, C.c_uint8))
+
+    def copy_game(self, dst, other, src):
+        lib().hs_copy_game(self.h, int(dst), other.h, int(src))
 
     def flags(self, game):
         return lib().hs_flags(self.h, game)

@@ -28,8 +28,10 @@ def reference_python():
 
 
 class RefVector:
-    def __init__(self, n_games, height=22, width=10, pieces=(0, 1, 2, 3, 4, 5, 6), n_players=2, variant="B"):
-        self.mod, self.set_time = refmod.load(variant)
+    def __init__(self, n_games, height=22, width=10, pieces=(0, 1, 2, 3, 4, 5, 6), n_players=2, variant="B", backend=None):
+        """backend: (module, set_time) of any tetris_env-shaped module (the per-env facade of b200tetris); default = the compiled
+        reference"""
+        self.mod, self.set_time = backend if backend is not None else refmod.load(variant)
         self.n, self.H, self.W, self.P = n_games, height, width, n_players
         self.map = (list(pieces) * 7)[:7]
         self.mod.set_pieces(self.map)

@@ -31,12 +31,14 @@ def test_struct_sizes_match_header_layout(tmp_path):
     import subprocess
     from b200tetris import _lib
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "b200tetris.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n",'
-                   'sizeof(b2t_config),sizeof(b2t_info),sizeof(b2t_obs),sizeof(b2t_step_args),sizeof(b2t_expand_args));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include "b200tetris.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(b2t_config),sizeof(b2t_info),sizeof(b2t_obs),sizeof(b2t_step_args),sizeof(b2t_expand_args),'
+                   'sizeof(b2t_player_raw),sizeof(b2t_game_raw));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.dirname(HEADER), str(src), "-o", str(exe)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
-    assert sizes == [C.sizeof(_lib.Config), C.sizeof(_lib.Info), C.sizeof(_lib.Obs), C.sizeof(_lib.StepArgs), C.sizeof(_lib.ExpandArgs)]
+    assert sizes == [C.sizeof(_lib.Config), C.sizeof(_lib.Info), C.sizeof(_lib.Obs), C.sizeof(_lib.StepArgs), C.sizeof(_lib.ExpandArgs),
+                     C.sizeof(_lib.PlayerRaw), C.sizeof(_lib.GameRaw)]
 
 
 def test_no_cpu_fallback():
