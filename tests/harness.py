@@ -54,7 +54,8 @@ def heuristic(field_after_lock):
 class Policy:
     """kind: 'random' (uniform over the de-duplicated placement list), 'greedy' (world-model heuristic with
     epsilon-random), 'junk' (random key strings incl. invalid keys and keys after a hard drop),
-    'sventon' (the [8]*r+[2]+[3]*t+[7] strings of agents/sventon_agent/sventon_utils.py:9-13)."""
+    'sventon' (the [8]*r+[2]+[3]*t+[7] strings of agents/sventon_agent/sventon_utils.py:9-13), 'press_key' (one key per step,
+    the action_type="press_key" mode: pieces come down by gravity and lock by the lockdown timer)."""
 
     def __init__(self, kind, kmax=64, lmax=32, eps=0.05, salt=1, solo_period=0):
         self.kind, self.kmax, self.lmax, self.eps, self.salt, self.solo_period = kind, kmax, lmax, eps, salt, solo_period
@@ -73,6 +74,12 @@ class Policy:
             for j in range(self.lmax):
                 keys[:, j] = (splitmix64(self.salt + 77, gids, t * 64 + j) % np.uint64(13)).astype(np.uint8)
             return keys, ln, None
+        if self.kind == "press_key":   # action_type "press_key" (tetris_environment.py:84-85): ONE key 0..10 per perform_action
+            keys = np.zeros((n, self.lmax), np.uint8)
+            k = (h % np.uint64(16)).astype(np.uint8)
+            # weighted towards moves and soft drops so pieces travel before gravity / lockdown / an occasional hard drop ends them
+            keys[:, 0] = np.array([0, 1, 3, 5, 5, 8, 9, 10, 1, 3, 5, 2, 4, 6, 7, 5], np.uint8)[k]
+            return keys, np.ones(n, np.uint8), None
         if self.kind == "sventon":
             W = lead.W
             r = (h % np.uint64(4)).astype(int)

@@ -19,6 +19,8 @@ ROLLOUTS = [
     ("greedy", 22, 10, ALL7, 32, 300, 23),
     ("junk", 22, 10, ALL7, 64, 300, 11),
     ("sventon", 22, 10, ALL7, 64, 150, 0),
+    ("press_key", 22, 10, ALL7, 64, 700, 0),     # action_type "press_key": one key per step, gravity / lockdown place the pieces
+    ("press_key", 16, 8, (0, 6), 32, 500, 30),
     ("random", 16, 8, (0, 6), 96, 200, 0),
     ("greedy", 16, 8, (0, 6), 32, 300, 0),
     ("random", 40, 20, ALL7, 40, 200, 0),

@@ -21,6 +21,8 @@ CASES = [
     ("greedy", 22, 10, (0, 1, 2, 3, 4, 5, 6), 8, 500, 23),
     ("junk", 22, 10, (0, 1, 2, 3, 4, 5, 6), 16, 400, 11),
     ("sventon", 22, 10, (0, 1, 2, 3, 4, 5, 6), 16, 200, 0),
+    ("press_key", 22, 10, (0, 1, 2, 3, 4, 5, 6), 16, 700, 0),
+    ("press_key", 16, 8, (0, 6), 8, 500, 30),
     ("random", 16, 8, (0, 6), 16, 300, 0),
     ("greedy", 16, 8, (0, 6), 8, 500, 0),
     ("random", 40, 20, (0, 1, 2, 3, 4, 5, 6), 4, 300, 0),

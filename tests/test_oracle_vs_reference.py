@@ -18,6 +18,9 @@ CASES = [
     ("greedy", 22, 10, (0, 1, 2, 3, 4, 5, 6), 4, 300, 23),   # same side repeats -> lockdown / gravity paths
     ("junk", 22, 10, (0, 1, 2, 3, 4, 5, 6), 8, 220, 11),
     ("sventon", 22, 10, (0, 1, 2, 3, 4, 5, 6), 8, 160, 0),
+    ("press_key", 22, 10, (0, 1, 2, 3, 4, 5, 6), 8, 700, 0),   # action_type "press_key": gravity / lockdown do the placing
+    ("press_key", 22, 10, (0, 1, 2, 3, 4, 5, 6), 4, 500, 40),
+    ("press_key", 16, 8, (0, 6), 4, 400, 0),
     ("random", 16, 8, (0, 6), 8, 200, 0),
     ("greedy", 16, 8, (0, 6), 6, 300, 0),
     ("random", 40, 20, (0, 1, 2, 3, 4, 5, 6), 3, 200, 0),
