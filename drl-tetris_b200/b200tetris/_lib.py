@@ -9,6 +9,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B2T_LIB") or os.path.join(_HERE, "libb200tetris.so")   # B2T_LIB: experimental builds (build.py --out)
 
 VEC_LEN = 19
+U8, F16, BF16, F32 = 0, 1, 2, 3   # b2t_dtype
+FLAG_TILES = 1                    # b2t_config.flags
 SNAPSHOT_SLOTS = 4
 
 OK, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4, -5
@@ -24,11 +26,12 @@ class Config(C.Structure):
 
 
 class Info(C.Structure):
-    _fields_ = [("kmax", C.c_int32), ("lmax", C.c_int32), ("state_bytes", C.c_int32), ("obs_bytes", C.c_int32)]
+    _fields_ = [("kmax", C.c_int32), ("lmax", C.c_int32), ("state_bytes", C.c_int32), ("obs_bytes", C.c_int32),
+                ("tile_bytes", C.c_int32)]
 
 
 class Obs(C.Structure):
-    _fields_ = [("d_field", vp), ("d_vec", vp), ("d_piece_idx", vp), ("d_scalars", vp), ("perspective", C.c_int32), ("d_me", vp)]
+    _fields_ = [("d_field", vp), ("d_vec", vp), ("d_piece_idx", vp), ("d_scalars", vp), ("perspective", C.c_int32), ("d_me", vp), ("dtype", C.c_int32)]
 
 
 class StepArgs(C.Structure):

@@ -34,7 +34,8 @@ def _np(a, dtype, n=None):
 
 class Engine:
     def __init__(self, n_games, height=22, width=10, pieces=(0, 1, 2, 3, 4, 5, 6), n_players=2, bar_null_moves=True,
-                 time_ms_per_action=400, piece_stream_len=0, hole_stream_len=0, device=0):
+                 time_ms_per_action=400, piece_stream_len=0, hole_stream_len=0, device=0, tiles=False):
+        """tiles: keep the raw cell values 1..8 of states[p].field (B2T_FLAG_TILES) — get_game / set_game then carry colours"""
         self._h = None
         self.lib = _lib.load()
         self.n, self.H, self.W, self.P = int(n_games), int(height), int(width), int(n_players)
@@ -46,7 +47,7 @@ class Engine:
         cfg.bar_null_moves = 1 if bar_null_moves else 0
         cfg.time_ms_per_action = int(time_ms_per_action)
         cfg.piece_stream_len, cfg.hole_stream_len = int(piece_stream_len), int(hole_stream_len)
-        cfg.device, cfg.flags = self.device, 0
+        cfg.device, cfg.flags = self.device, (_lib.FLAG_TILES if tiles else 0)
         h = C.c_void_p()
         rc = self.lib.b2t_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -225,7 +226,18 @@ class Engine:
         o = _lib.Obs()
         o.d_field, o.d_vec, o.d_piece_idx, o.d_scalars = (self._dp(field), self._dp(vec), self._dp(piece_idx), self._dp(scalars))
         o.perspective, o.d_me = int(bool(perspective)), self._dp(me)
+        o.dtype = self._dtype_of(field, vec)
         return o
+
+    @staticmethod
+    def _dtype_of(field, vec):
+        """b2t_dtype from the torch dtype of the field / vec tensors (they must agree)"""
+        import torch
+        codes = {torch.uint8: _lib.U8, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16, torch.float32: _lib.F32}
+        kinds = {codes[t.dtype] for t in (field, vec) if t is not None}
+        if len(kinds) > 1:
+            raise ValueError("field and vec must have the same dtype")
+        return kinds.pop() if kinds else _lib.U8
 
     def select_dev(self, scores, offsets, placement):
         """argmax of per-placement scores within every board of the last expand_dev -> placement indices for step_dev"""

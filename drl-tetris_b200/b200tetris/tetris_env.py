@@ -24,8 +24,8 @@ What is reproduced (reference file:line):
                                       scripts/eval.py:156) reach the device.  Views are snapshots: re-read after stepping.
   .last_winner / .recreate_state()    PythonHandle.h:315,319
   pickling                            PythonHandle.h:283-308   (unlike the reference the RNG position survives a pickle)
-Not reproduced: tile colours in `field` (cells read 1 where the reference has 1..8; only `field > 0` is observable through
-state_dict) and n_players != 2.
+Tile colours in `field` (1..7 = piece.tile, 8 = garbage) are kept after set_tile_colours(True) (B2T_FLAG_TILES); by default cells
+read 1 where the reference has 1..8 — only `field > 0` is observable through state_dict.  Not reproduced: n_players != 2.
 """
 import gc
 import time as _time_mod
@@ -35,12 +35,13 @@ import numpy as np
 from . import _lib
 from .engine import Engine
 
-__all__ = ["set_pieces", "PythonHandle", "State", "Mask", "set_time_source", "set_device", "set_arena_slots"]
+__all__ = ["set_pieces", "PythonHandle", "State", "Mask", "set_time_source", "set_device", "set_arena_slots", "set_tile_colours"]
 
 _pieces = [0, 1, 2, 3, 4, 5, 6]   # GamePlay::randomizer_map (gamePlay.cpp:9)
 _time = _time_mod.time            # what time(NULL) returns
 _device = 0
 _slots = 4096                     # game slots per arena chunk
+_tiles = False                    # keep raw cell values 1..8 (B2T_FLAG_TILES) for handles created afterwards
 _arenas = {}
 _engine_factory = Engine          # tests substitute a CPU double with the same small interface; the product has no CPU path
 
@@ -64,6 +65,12 @@ def set_device(device):
     _device = int(device)
 
 
+def set_tile_colours(on):
+    """states[p].field then reads 1..7 (piece.tile) / 8 (garbage) like the reference's (renderer, raw-field parity) instead of 1."""
+    global _tiles
+    _tiles = bool(on)
+
+
 def set_arena_slots(n):
     global _slots
     _slots = int(n)
@@ -72,17 +79,17 @@ def set_arena_slots(n):
 class _Arena:
     """Game slots of one (field size, piece map, device): a list of engine chunks and a free list of (chunk, slot)."""
 
-    def __init__(self, H, W, pieces, device):
-        self.key = (H, W, tuple(pieces), device)
+    def __init__(self, H, W, pieces, device, tiles=False):
+        self.key = (H, W, tuple(pieces), device, tiles)
         self.chunks, self.free = [], []
 
     def alloc(self):
         if not self.free and self.chunks:
             gc.collect()     # handles and their State objects reference each other: dropped copies free their slots here
         if not self.free:
-            H, W, pieces, device = self.key
+            H, W, pieces, device, tiles = self.key
             n = _slots * (1 << min(len(self.chunks), 4))
-            eng = _engine_factory(n, H, W, pieces, 2, True, 400, device=device)
+            eng = _engine_factory(n, H, W, pieces, 2, True, 400, device=device, tiles=tiles)
             self.chunks.append(eng)
             self.free.extend((eng, s) for s in range(n - 1, 0, -1))   # slot 0 stays a never-reset game: the template of new handles
         return self.free.pop()
@@ -92,7 +99,7 @@ class _Arena:
 
 
 def _arena(H, W):
-    key = (int(H), int(W), tuple(_pieces), _device)
+    key = (int(H), int(W), tuple(_pieces), _device, _tiles)
     a = _arenas.get(key)
     if a is None:
         a = _arenas[key] = _Arena(*key)
@@ -241,7 +248,7 @@ class PythonHandle:
     def _write(self, player, name, value):
         raw, field = self._raw()
         if name == "field":
-            field[player] = (np.asarray(value) != 0)
+            field[player] = np.asarray(value) if self._arena.key[4] else (np.asarray(value) != 0)
             self._eng.set_game(self._slot, raw, field)
         elif name in _FIELDS:
             setattr(raw.player[player], _FIELDS[name][0], int(np.asarray(value).ravel()[0]))

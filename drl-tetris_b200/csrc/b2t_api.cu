@@ -65,6 +65,10 @@ struct b2t_handle {
     double* powtab = nullptr;
     unsigned long long* stats = nullptr;
     uint4* xfer = nullptr;   // one game's vectors for export/import
+    uint32_t* tiles = nullptr;          // colour planes (B2T_FLAG_TILES)
+    uint32_t* snap_tiles[B2T_SNAPSHOT_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t* xfer_tiles = nullptr;
+    size_t tile_words_total = 0;
     DevTabs tabs;
     Arena in, out;
     bool enumerated = false;
@@ -94,6 +98,8 @@ int b2t_destroy(b2t_handle* h) {
     cudaSetDevice(h->cfg.device);
     cudaFree(h->state);
     for (auto s : h->snap) cudaFree(s);
+    for (auto s : h->snap_tiles) cudaFree(s);
+    cudaFree(h->tiles); cudaFree(h->xfer_tiles);
     cudaFree(h->plc); cudaFree(h->kcache); cudaFree(h->scan_sums); cudaFree(h->d_total); cudaFree(h->row_meta);
     cudaFree(h->piece_tab); cudaFree(h->hole_tab); cudaFree(h->powtab); cudaFree(h->stats); cudaFree(h->xfer);
     h->in.release(); h->out.release();
@@ -143,6 +149,12 @@ int b2t_create(const b2t_config* cfg, b2t_handle** out) {
     CKC(cudaMalloc((void**)&h->stats, STAT_SLICES * STAT_WORDS * sizeof(unsigned long long)));
     CKC(cudaMemset(h->stats, 0, STAT_SLICES * STAT_WORDS * sizeof(unsigned long long)));
     CKC(cudaMalloc((void**)&h->xfer, (size_t)ops->NV * sizeof(uint4)));
+    if (cfg->flags & B2T_FLAG_TILES) {
+        h->tile_words_total = (size_t)ops->tile_words * 32 * ((n + 31) / 32);
+        CKC(cudaMalloc((void**)&h->tiles, h->tile_words_total * sizeof(uint32_t)));
+        CKC(cudaMemset(h->tiles, 0, h->tile_words_total * sizeof(uint32_t)));
+        CKC(cudaMalloc((void**)&h->xfer_tiles, (size_t)ops->tile_words * sizeof(uint32_t)));
+    }
     const size_t plen = (size_t)h->cfg.piece_stream_len, hlen = (size_t)h->cfg.hole_stream_len;
     CKC(cudaMalloc((void**)&h->piece_tab, plen * RNG_SEEDS));
     CKC(cudaMalloc((void**)&h->hole_tab, hlen * RNG_SEEDS));
@@ -181,22 +193,24 @@ int b2t_get_info(const b2t_handle* h, b2t_info* out) {
     out->kmax = h->ops->KMAX; out->lmax = h->ops->LMAX;
     out->state_bytes = h->ops->NV * 16;
     out->obs_bytes = 2 * (h->ops->H * h->ops->W + B2T_VEC_LEN + 1);
+    out->tile_bytes = h->tiles ? h->ops->tile_words * 4 : 0;
     return B2T_OK;
 }
 
 static void base_params(b2t_handle* h, KParams& p) {
     memset(&p, 0, sizeof p);
-    p.state = h->state; p.n_games = h->cfg.n_games; p.tabs = h->tabs; p.stats = h->stats;
+    p.state = h->state; p.tiles = h->tiles; p.n_games = h->cfg.n_games; p.tabs = h->tabs; p.stats = h->stats;
     p.plc = h->plc; p.kcache = h->kcache; p.elapsed = h->cfg.time_ms_per_action;
 }
 static int check_obs(b2t_handle* h, const b2t_obs& o) {
     if (!aligned16(o.d_field) || !aligned16(o.d_vec) || !aligned16(o.d_piece_idx) || !aligned16(o.d_scalars))
         return fail(h, B2T_ERR_ARG, "observation pointers must be 16-byte aligned%s");
+    if (o.dtype < B2T_U8 || o.dtype > B2T_F32) return fail(h, B2T_ERR_ARG, "b2t_obs.dtype must be B2T_U8, B2T_F16, B2T_BF16 or B2T_F32%s");
     return B2T_OK;
 }
 static void set_obs(KParams& p, const b2t_obs& o) {
-    p.field = o.d_field; p.vec = o.d_vec; p.piece_idx = o.d_piece_idx; p.scalars = o.d_scalars;
-    p.perspective = o.perspective ? 1 : 0; p.me = o.d_me;
+    p.field = (uint8_t*)o.d_field; p.vec = (uint8_t*)o.d_vec; p.piece_idx = o.d_piece_idx; p.scalars = o.d_scalars;
+    p.perspective = o.perspective ? 1 : 0; p.me = o.d_me; p.obs_dtype = o.dtype;
 }
 
 int b2t_reset(b2t_handle* h, const int32_t* d_idx, int32_t n, const uint32_t* d_seeds, void* stream) {
@@ -315,12 +329,17 @@ int b2t_snapshot(b2t_handle* h, int32_t slot, void* stream) {
     CK(cudaSetDevice(h->cfg.device));
     if (!h->snap[slot]) CK(cudaMalloc((void**)&h->snap[slot], h->state_vecs * sizeof(uint4)));
     CK(cudaMemcpyAsync(h->snap[slot], h->state, h->state_vecs * sizeof(uint4), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    if (h->tiles) {
+        if (!h->snap_tiles[slot]) CK(cudaMalloc((void**)&h->snap_tiles[slot], h->tile_words_total * sizeof(uint32_t)));
+        CK(cudaMemcpyAsync(h->snap_tiles[slot], h->tiles, h->tile_words_total * sizeof(uint32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
     return B2T_OK;
 }
 int b2t_restore(b2t_handle* h, int32_t slot, void* stream) {
     if (!h || slot < 0 || slot >= B2T_SNAPSHOT_SLOTS || !h->snap[slot]) return fail(h, B2T_ERR_ARG, "b2t_restore: bad or empty slot%s");
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaMemcpyAsync(h->state, h->snap[slot], h->state_vecs * sizeof(uint4), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    if (h->tiles) CK(cudaMemcpyAsync(h->tiles, h->snap_tiles[slot], h->tile_words_total * sizeof(uint32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return B2T_OK;
 }
 
@@ -345,11 +364,20 @@ int b2t_import_state(b2t_handle* h, int32_t game, const void* h_buf, void* strea
     return B2T_OK;
 }
 
+static int fetch_tiles(b2t_handle* h, int32_t game, std::vector<uint32_t>& planes) {
+    planes.assign((size_t)h->ops->tile_words, 0u);
+    gather_tiles_kernel<<<(h->ops->tile_words + 63) / 64, 64>>>(h->tiles, game, h->ops->tile_words, h->xfer_tiles);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(planes.data(), h->xfer_tiles, planes.size() * 4, cudaMemcpyDeviceToHost));
+    return B2T_OK;
+}
 int b2t_get_game(b2t_handle* h, int32_t game, b2t_game_raw* out, uint8_t* h_field) {
     if (!h || !out || game < 0 || game >= h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_get_game: bad argument%s");
-    std::vector<uint32_t> words((size_t)h->ops->NV * 4);
+    std::vector<uint32_t> words((size_t)h->ops->NV * 4), planes;
     if (int r = b2t_export_state(h, game, words.data(), nullptr)) return r;
-    h->ops->decode(words.data(), out, h_field);
+    if (h->tiles && h_field)
+        if (int r = fetch_tiles(h, game, planes)) return r;
+    h->ops->decode(words.data(), out, h_field, planes.empty() ? nullptr : planes.data());
     return B2T_OK;
 }
 int b2t_set_game(b2t_handle* h, int32_t game, const b2t_game_raw* in, const uint8_t* h_field) {
@@ -357,9 +385,15 @@ int b2t_set_game(b2t_handle* h, int32_t game, const b2t_game_raw* in, const uint
     for (int p = 0; p < 2; p++)
         if (in->player[p].piece_kind < 0 || in->player[p].piece_kind > 7 || in->player[p].nextpiece < 0 || in->player[p].nextpiece > 7)
             return fail(h, B2T_ERR_ARG, "b2t_set_game: piece_kind / nextpiece out of range%s");
-    std::vector<uint32_t> words((size_t)h->ops->NV * 4);
+    std::vector<uint32_t> words((size_t)h->ops->NV * 4), planes;
     if (int r = b2t_export_state(h, game, words.data(), nullptr)) return r;
-    h->ops->encode(words.data(), in, h_field);
+    if (h->tiles && h_field) planes.assign((size_t)h->ops->tile_words, 0u);
+    h->ops->encode(words.data(), in, h_field, planes.empty() ? nullptr : planes.data());
+    if (!planes.empty()) {
+        CK(cudaMemcpy(h->xfer_tiles, planes.data(), planes.size() * 4, cudaMemcpyHostToDevice));
+        scatter_tiles_kernel<<<(h->ops->tile_words + 63) / 64, 64>>>(h->tiles, game, h->ops->tile_words, h->xfer_tiles);
+        CK(cudaGetLastError());
+    }
     return b2t_import_state(h, game, words.data(), nullptr);
 }
 int b2t_copy_game(b2t_handle* to, int32_t dst, b2t_handle* from, int32_t src, void* stream) {
@@ -370,6 +404,8 @@ int b2t_copy_game(b2t_handle* to, int32_t dst, b2t_handle* from, int32_t src, vo
         return fail(h, B2T_ERR_ARG, "b2t_copy_game: handles differ in field size or device%s");
     CK(cudaSetDevice(h->cfg.device));
     copy_game_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(to->state, dst, from->state, src, h->ops->NV);
+    if (to->tiles)   // colours travel with the game (a source without planes reads as all ones)
+        copy_tiles_kernel<<<(h->ops->tile_words + 63) / 64, 64, 0, (cudaStream_t)stream>>>(to->tiles, dst, from->tiles, src, h->ops->tile_words);
     CK(cudaGetLastError());
     return B2T_OK;
 }

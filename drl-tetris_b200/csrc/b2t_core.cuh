@@ -216,8 +216,19 @@ template <class G, int S> struct Board {
     typedef typename G::col_t col_t;
     col_t* cols;        // column c at cols[(c + XL) * S]
     uint32_t* stream;   // word w at stream[w * S]
+    // Optional tile-colour planes (b2t_config.flags & B2T_FLAG_TILES): the raw cell values 1..8 of PythonHandle.states[p].field
+    // (piece.tile = piece + 1, gameField.cpp:105-110; garbage = 8, gamePlay.cpp:202) as three bit streams of (value - 1) in the
+    // stream's bit order, word w of plane k at tiles[(k*SW + w) * S].  nullptr (the default) = occupancy only.
+    uint32_t* tiles = nullptr;
     B2T_HD col_t& col(int c) const { return cols[(c + G::XL) * S]; }
     B2T_HD uint32_t& sw(int w) const { return stream[w * S]; }
+    B2T_HD uint32_t& tw(int k, int w) const { return tiles[(k * G::SW + w) * S]; }
+};
+constexpr int TILE_PLANES = 3;
+// accessors so that one routine shifts the occupancy stream and every colour plane alike
+template <class G, int S> struct StreamRef {
+    uint32_t* p;
+    B2T_HD uint32_t& operator()(int w) const { return p[w * S]; }
 };
 
 template <class G, int S> B2T_HD void board_init_walls(const Board<G, S>& b) {
@@ -227,6 +238,8 @@ template <class G, int S> B2T_HD void board_init_walls(const Board<G, S>& b) {
 template <class G, int S> B2T_HD void board_clear(const Board<G, S>& b) {
     for (int c = 0; c < G::W; c++) b.col(c) = G::empty_col();
     for (int w = 0; w < G::SW; w++) b.sw(w) = 0;
+    if (b.tiles)
+        for (int w = 0; w < TILE_PLANES * G::SW; w++) b.tiles[w * S] = 0;
 }
 
 // gameField.cpp:10-20 possible(): pcn = column nibbles of the piece at its rotation
@@ -263,7 +276,7 @@ template <class G, int S> B2T_HD typename G::col_t collide_mask(const Board<G, S
 template <class G> B2T_HD int rest_from(typename G::col_t cm, int y) { return y + ctz((typename G::col_t)(cm >> (y + G::YB + 1))); }
 
 // gameField.cpp:105-110 addPiece (occupancy only) — columns and stream
-template <class G, int S> B2T_HD void stamp(const Board<G, S>& b, int x, int y, uint32_t pcn, uint32_t pcc) {
+template <class G, int S> B2T_HD void stamp(const Board<G, S>& b, int x, int y, uint32_t pcn, uint32_t pcc, int kind) {
     typedef typename G::col_t col_t;
     col_t* p = b.cols + (x + G::XL) * S;
     const int sh = y + G::YB;
@@ -277,7 +290,60 @@ template <class G, int S> B2T_HD void stamp(const Board<G, S>& b, int x, int y, 
         int cx = (pcc >> (4 * i)) & 3, cy = (pcc >> (4 * i + 2)) & 3;
         int bit = (y + cy) * G::W + x + cx;
         b.sw(bit >> 5) |= 1u << (bit & 31);
+        if (b.tiles)                                   // cell value = piece.tile = kind + 1: the planes hold `kind`; a piece that
+            for (int k = 0; k < TILE_PLANES; k++) {    // dies on spawn overwrites the cells it overlaps (gameField.cpp:105-110)
+                uint32_t& t = b.tw(k, bit >> 5);
+                t = (t & ~(1u << (bit & 31))) | ((uint32_t)((kind >> k) & 1) << (bit & 31));
+            }
     }
+}
+
+// row r of a row-major bit stream disappears: bits [0, r*W) move up by W, bits [(r+1)*W, ..) stay
+template <class G, class A> B2T_HD void stream_remove_row(A sw, int r) {
+    const int cut = r * G::W, end = cut + G::W;
+    uint32_t prev = 0;  // bits shifted out of the previous (lower) word
+    for (int w = 0; w < G::SW; w++) {
+        const int lo = w * 32;
+        uint32_t v = sw(w);
+        // part of this word below `cut`
+        uint32_t mlow = cut <= lo ? 0u : (cut >= lo + 32 ? 0xFFFFFFFFu : ((1u << (cut - lo)) - 1u));
+        uint32_t mkeep = end <= lo ? 0xFFFFFFFFu : (end >= lo + 32 ? 0u : ~((1u << (end - lo)) - 1u));
+        uint32_t lowpart = v & mlow;
+        uint32_t shifted;
+        if (G::W < 32) shifted = (lowpart << G::W) | prev;
+        else shifted = prev;
+        uint32_t nprev = (G::W < 32) ? (lowpart >> (32 - G::W)) : lowpart;
+        // shifted bits may only land below `end`
+        uint32_t mdst = end <= lo ? 0u : (end >= lo + 32 ? 0xFFFFFFFFu : ((1u << (end - lo)) - 1u));
+        sw(w) = (v & mkeep) | (shifted & mdst);
+        prev = nprev;
+    }
+}
+// every row moves up by one (the top row is lost) and `row` becomes the bottom row
+template <class G, class A> B2T_HD void stream_push_row(A sw, uint32_t row) {
+    for (int w = 0; w < G::SW; w++) {
+        uint32_t v = sw(w), nx = (w + 1 < G::SW) ? sw(w + 1) : 0u;
+        sw(w) = (G::W < 32) ? ((v >> G::W) | (nx << (32 - G::W))) : nx;
+    }
+    const int bit = (G::H - 1) * G::W;
+    const int total = G::H * G::W;
+    for (int w = bit >> 5; w < G::SW; w++) {
+        const int lo = w * 32;
+        uint32_t ins = (lo >= bit) ? (row >> (lo - bit)) : (row << (bit - lo));
+        uint32_t m = 0xFFFFFFFFu;
+        if (lo < bit) m &= ~((1u << (bit - lo)) - 1u);
+        if (total < lo + 32) m &= (1u << (total - lo)) - 1u;
+        sw(w) = (sw(w) & ~m) | (ins & m);
+    }
+}
+template <class G, class A> B2T_HD uint32_t stream_bottom_row(A sw) {   // the W bits of row H-1
+    const int bit = (G::H - 1) * G::W;
+    uint32_t row = 0;
+    for (int w = bit >> 5; w < G::SW; w++) {
+        const int lo = w * 32;
+        row |= (lo >= bit) ? (sw(w) << (lo - bit)) : (sw(w) >> (bit - lo));
+    }
+    return row & ((G::W < 32) ? ((1u << G::W) - 1u) : 0xFFFFFFFFu);
 }
 
 // remove one row: everything above slides down, row 0 becomes empty (gameField.cpp:112-118)
@@ -289,25 +355,9 @@ template <class G, int S> B2T_HD void remove_row(const Board<G, S>& b, int r) {
         col_t v = b.col(c);
         b.col(c) = (col_t)((v & keep) | ((v & low) << 1) | G::ceil_mask());
     }
-    // stream: bits [0, r*W) move up by W, bits [(r+1)*W, ..) stay
-    const int cut = r * G::W, end = cut + G::W;
-    uint32_t prev = 0;  // bits shifted out of the previous (lower) word
-    for (int w = 0; w < G::SW; w++) {
-        const int lo = w * 32;
-        uint32_t v = b.sw(w);
-        // part of this word below `cut`
-        uint32_t mlow = cut <= lo ? 0u : (cut >= lo + 32 ? 0xFFFFFFFFu : ((1u << (cut - lo)) - 1u));
-        uint32_t mkeep = end <= lo ? 0xFFFFFFFFu : (end >= lo + 32 ? 0u : ~((1u << (end - lo)) - 1u));
-        uint32_t lowpart = v & mlow;
-        uint32_t shifted;
-        if (G::W < 32) shifted = (lowpart << G::W) | prev;
-        else shifted = prev;
-        uint32_t nprev = (G::W < 32) ? (lowpart >> (32 - G::W)) : lowpart;
-        // shifted bits may only land below `end`
-        uint32_t mdst = end <= lo ? 0u : (end >= lo + 32 ? 0xFFFFFFFFu : ((1u << (end - lo)) - 1u));
-        b.sw(w) = (v & mkeep) | (shifted & mdst);
-        prev = nprev;
-    }
+    stream_remove_row<G>(StreamRef<G, S>{b.stream}, r);
+    if (b.tiles)
+        for (int k = 0; k < TILE_PLANES; k++) stream_remove_row<G>(StreamRef<G, S>{b.tiles + k * G::SW * S}, r);
 }
 
 // gameField.cpp:120-145 clearlines(): rows posY..H-1, bottom-up with re-check  ==  repeatedly remove the lowest full row
@@ -344,21 +394,16 @@ template <class G, int S> B2T_HD void garbage_row(const Board<G, S>& b, int hole
     uint32_t row = old_row;
     row |= (G::W >= 10) ? 0x3FFu : ((1u << G::W) - 1u);
     if (hole < G::W) row &= ~(1u << hole);
-    // stream >>= W, then insert `row` at (H-1)*W
-    for (int w = 0; w < G::SW; w++) {
-        uint32_t v = b.sw(w), nx = (w + 1 < G::SW) ? b.sw(w + 1) : 0u;
-        b.sw(w) = (G::W < 32) ? ((v >> G::W) | (nx << (32 - G::W))) : nx;
+    if (b.tiles) {   // rows move up keeping their colours; columns 0..9 of the new bottom row become 8 (planes: 7), the rest keep the old bottom row
+        const uint32_t grey = ((G::W >= 10) ? 0x3FFu : ((1u << G::W) - 1u)) & ((hole < G::W) ? ~(1u << hole) : 0xFFFFFFFFu);
+        for (int k = 0; k < TILE_PLANES; k++) {
+            StreamRef<G, S> pl{b.tiles + k * G::SW * S};
+            uint32_t keep = stream_bottom_row<G>(pl) & ~0x3FFu;
+            if (hole < G::W) keep &= ~(1u << hole);
+            stream_push_row<G>(pl, keep | grey);
+        }
     }
-    const int bit = (G::H - 1) * G::W;
-    const int total = G::H * G::W;
-    for (int w = bit >> 5; w < G::SW; w++) {
-        const int lo = w * 32;
-        uint32_t ins = (lo >= bit) ? (row >> (lo - bit)) : (row << (bit - lo));
-        uint32_t m = 0xFFFFFFFFu;
-        if (lo < bit) m &= ~((1u << (bit - lo)) - 1u);
-        if (total < lo + 32) m &= (1u << (total - lo)) - 1u;
-        b.sw(w) = (b.sw(w) & ~m) | (ins & m);
-    }
+    stream_push_row<G>(StreamRef<G, S>{b.stream}, row);
 }
 
 // ------------------------------------------------------------------------------------------------ player scalars
@@ -554,7 +599,7 @@ template <class G, int S> B2T_HD bool make_new_piece(PS& s, const Board<G, S>& b
     s.next = tb.piece[(size_t)seed16 * tb.piece_len + at];
     s.piece_ctr++;
     const uint32_t pcn = pcn_of(tb, s.kind, s.rot);
-    if (!fits<G, S>(b, s.x, s.y, pcn)) { stamp<G, S>(b, s.x, s.y, pcn, pcc_of(tb, s.kind, s.rot)); return true; }
+    if (!fits<G, S>(b, s.x, s.y, pcn)) { stamp<G, S>(b, s.x, s.y, pcn, pcc_of(tb, s.kind, s.rot), (int)s.kind); return true; }
     return false;
 }
 // gamePlay.cpp:160-171 sendLines
@@ -570,7 +615,7 @@ template <class G, int S, class ST> B2T_HD void hd_make(ST& s, const Board<G, S>
     if (s.kind > 6) return;
     const uint32_t pcc = pcc_of(tb, s.kind, s.rot);
     s.y = rest_from<G>(collide_mask<G, S>(b, s.x, pcc), s.y);
-    stamp<G, S>(b, s.x, s.y, pcn_of(tb, s.kind, s.rot), pcc);
+    stamp<G, S>(b, s.x, s.y, pcn_of(tb, s.kind, s.rot), pcc, (int)s.kind);
     dd_reset(s, s.time_ms);
 }
 // gamePlay.cpp:54-59 hd_finish: -1 = died

@@ -92,6 +92,7 @@ B2T_HD bool game_perform(Game<G, S>& g, const Tabs& tb, int player, const uint32
         Board<G, S> bb;
         bb.cols = one ? g.b[1].cols : g.b[0].cols;
         bb.stream = one ? g.b[1].stream : g.b[0].stream;
+        bb.tiles = one ? g.b[1].tiles : g.b[0].tiles;
         if (!dead) {
             apply_keys<G, S, KS>(me, bb, tb, keys, nkeys);
 #pragma unroll

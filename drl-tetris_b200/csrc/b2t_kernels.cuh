@@ -5,6 +5,7 @@
 // in shared memory and every lane expands 16 bits -> one 128-bit store, so the [rows,2,H,W] tensor is written fully
 // coalesced no matter how H*W aligns.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "b2t_game.cuh"
@@ -44,6 +45,7 @@ enum : uint32_t {
 
 struct KParams {
     uint4* state;
+    uint32_t* tiles;              // optional colour planes [n_tiles][2*TILE_PLANES*SW][32] (B2T_FLAG_TILES), generic variant only
     int32_t n_games;
     const int32_t* idx;
     int32_t n;
@@ -70,6 +72,7 @@ struct KParams {
     uint8_t* vec;
     uint8_t* piece_idx;
     int32_t* scalars;
+    int32_t obs_dtype;            // b2t_obs.dtype of field / vec: 0 uint8, 1 half, 2 bfloat16, 3 float
     int32_t perspective;          // 1: (me, opponent) order of the observation tensors
     const uint8_t* me;            // per-row perspective player for plain observe
     int32_t* board_of;            // KF_EXPAND
@@ -103,9 +106,28 @@ template <class G> struct SmemLayout {
 
 // ---------------------------------------------------------------------------------------------- cooperative outputs
 // wb: this warp's WB(+1) words.  Rows = lanes.  out = address of the warp's first row.
-template <class G>
+// B = bytes per output cell: 1 (uint8, the reference's state_dict dtype) or 2 / 4 (half / bfloat16 / float written directly for
+// the network, agents/agent_utils/state_unpack.py:88-105); `one` = the bit pattern of 1.0 in that type.
+template <int B> __device__ __forceinline__ uint4 expand_cells(uint32_t bits, uint32_t one) {
+    uint4 q;
+    if constexpr (B == 1) {          // 16 cells
+        q.x = ((bits & 15u) * 0x00204081u) & 0x01010101u;
+        q.y = (((bits >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+        q.z = (((bits >> 8) & 15u) * 0x00204081u) & 0x01010101u;
+        q.w = ((bits >> 12) * 0x00204081u) & 0x01010101u;
+    } else if constexpr (B == 2) {   // 8 cells, two per word
+        q.x = ((bits & 1u) | ((bits & 2u) << 15)) * one;
+        q.y = (((bits >> 2) & 1u) | ((bits & 8u) << 13)) * one;
+        q.z = (((bits >> 4) & 1u) | ((bits & 32u) << 11)) * one;
+        q.w = (((bits >> 6) & 1u) | ((bits & 128u) << 9)) * one;
+    } else {                         // 4 cells
+        q.x = (bits & 1u) ? one : 0u; q.y = (bits & 2u) ? one : 0u; q.z = (bits & 4u) ? one : 0u; q.w = (bits & 8u) ? one : 0u;
+    }
+    return q;
+}
+template <class G, int B = 1>
 __device__ __forceinline__ void emit_fields(uint32_t* wb, const Board<G, WS>& b0, const Board<G, WS>& b1, bool has_row,
-                                            uint8_t* out, int valid_rows, int lane) {
+                                            uint8_t* out, int valid_rows, int lane, uint32_t one = 1u) {
     constexpr int HW = G::H * G::W;
     constexpr int REM = HW & 31;                 // valid bits in a player's last stream word (0 = all 32)
     constexpr int RW = (2 * HW + 31) / 32;       // words of one row's record (player 0 bits, then player 1 bits)
@@ -143,42 +165,35 @@ __device__ __forceinline__ void emit_fields(uint32_t* wb, const Board<G, WS>& b0
         if (j >= first && j <= lastk) wb[wo + j] = v;
     }
     __syncwarp();
-    // 3. every lane expands 16 bits -> 16 bytes -> one 128-bit store
+    // 3. every lane expands 16 / 8 / 4 bits -> 16 bytes -> one 128-bit store
+    if constexpr (B != 1) {
+        constexpr int CPL = 16 / B;                // cells per store
+        constexpr int NCHW = 64 * HW / CPL;        // stores for 32 rows
+        const int valid_ch = valid_rows * 2 * HW / CPL;   // 2*HW*B is a multiple of 16 for B >= 2 whenever HW is even ...
+        static_assert((2 * G::H * G::W * B) % 16 == 0 || B == 1, "wide cells need 16-byte rows");
+        const uint8_t* bb = reinterpret_cast<const uint8_t*>(wb);
+        uint4* op = reinterpret_cast<uint4*>(out);
+        for (int c = lane; c < NCHW && c < valid_ch; c += 32) {
+            const uint32_t bits = (B == 2) ? bb[c] : ((bb[c >> 1] >> (4 * (c & 1))) & 15u);
+            op[c] = expand_cells<B>(bits, one);
+        }
+        __syncwarp();
+        return;
+    }
     const uint16_t* hb = reinterpret_cast<const uint16_t*>(wb);
     constexpr int NCH = 4 * HW;  // 16-byte chunks in 32 rows
     if (valid_rows == 32) {
         const uint16_t* hp = hb + lane;
         uint4* op = reinterpret_cast<uint4*>(out) + lane;
 #pragma unroll 4
-        for (int it = 0; it < NCH / 32; it++) {
-            const uint32_t h = hp[it * 32];
-            uint4 q;
-            q.x = ((h & 15u) * 0x00204081u) & 0x01010101u;
-            q.y = (((h >> 4) & 15u) * 0x00204081u) & 0x01010101u;
-            q.z = (((h >> 8) & 15u) * 0x00204081u) & 0x01010101u;
-            q.w = ((h >> 12) * 0x00204081u) & 0x01010101u;
-            op[it * 32] = q;
-        }
-        if ((NCH & 31) != 0 && lane < (NCH & 31)) {
-            const uint32_t h = hp[(NCH / 32) * 32];
-            uint4 q;
-            q.x = ((h & 15u) * 0x00204081u) & 0x01010101u;
-            q.y = (((h >> 4) & 15u) * 0x00204081u) & 0x01010101u;
-            q.z = (((h >> 8) & 15u) * 0x00204081u) & 0x01010101u;
-            q.w = ((h >> 12) * 0x00204081u) & 0x01010101u;
-            op[(NCH / 32) * 32] = q;
-        }
+        for (int it = 0; it < NCH / 32; it++) op[it * 32] = expand_cells<1>(hp[it * 32], 1u);
+        if ((NCH & 31) != 0 && lane < (NCH & 31)) op[(NCH / 32) * 32] = expand_cells<1>(hp[(NCH / 32) * 32], 1u);
     } else {
         const int valid_bytes = valid_rows * 2 * HW;
         for (int c = lane; c < NCH; c += 32) {
             const int byte0 = 16 * c;
             if (byte0 >= valid_bytes) break;
-            const uint32_t h = hb[c];
-            uint4 q;
-            q.x = ((h & 15u) * 0x00204081u) & 0x01010101u;
-            q.y = (((h >> 4) & 15u) * 0x00204081u) & 0x01010101u;
-            q.z = (((h >> 8) & 15u) * 0x00204081u) & 0x01010101u;
-            q.w = ((h >> 12) * 0x00204081u) & 0x01010101u;
+            const uint4 q = expand_cells<1>(hb[c], 1u);
             if (byte0 + 16 <= valid_bytes) {
                 *reinterpret_cast<uint4*>(out + byte0) = q;
             } else {
@@ -206,6 +221,13 @@ __device__ __forceinline__ void vec_words(const PS& s, uint32_t* w) {
     w[3] = (uint32_t)ohk;
     w[4] = (uint32_t)(ohk >> 32);
 }
+// DT: 0 uint8, 1 half, 2 bfloat16, 3 float (b2t_obs.dtype)
+template <int DT> __device__ __forceinline__ uint32_t cvt_small(uint32_t v) {   // exact: v <= 255
+    if constexpr (DT == 1) return (uint32_t)__half_as_ushort(__uint2half_rn(v));
+    else if constexpr (DT == 2) return __float_as_uint((float)v) >> 16;
+    else return __float_as_uint((float)v);
+}
+template <int DT = 0>
 __device__ __forceinline__ void emit_vecs(uint8_t* sv, const PS& p0, const PS& p1, bool swap, bool has_row, uint8_t* out, int valid_rows, int lane) {
     __syncwarp();   // staging aliases the warp's columns
     if (has_row) {
@@ -229,6 +251,30 @@ __device__ __forceinline__ void emit_vecs(uint8_t* sv, const PS& p0, const PS& p
         for (int k = 0; k < 19; k++) d16[k] = (uint16_t)(r[k >> 1] >> (16 * (k & 1)));
     }
     __syncwarp();
+    if constexpr (DT != 0) {     // the staged bytes widened on the way out: 8 (half / bfloat16) or 4 (float) values per 128-bit store
+        constexpr int B = (DT == 3) ? 4 : 2, CPL = 16 / B;
+        const int nval = valid_rows * 2 * VEC_LEN;
+        for (int c = lane; c * CPL < nval; c += 32) {
+            uint32_t v[CPL];
+#pragma unroll
+            for (int j = 0; j < CPL; j++) v[j] = cvt_small<DT>(sv[c * CPL + j]);   // (reads past the last row stay inside the staging area; the stores are guarded)
+            if ((c + 1) * CPL <= nval) {
+                uint4 q;
+                if constexpr (B == 4) { q.x = v[0]; q.y = v[1]; q.z = v[2]; q.w = v[3]; }
+                else { q.x = v[0] | (v[1] << 16); q.y = v[2] | (v[3] << 16); q.z = v[4] | (v[5] << 16); q.w = v[6] | (v[7] << 16); }
+                reinterpret_cast<uint4*>(out)[c] = q;
+            } else {
+#pragma unroll
+                for (int j = 0; j < CPL; j++)
+                    if (c * CPL + j < nval) {
+                        if constexpr (B == 4) reinterpret_cast<uint32_t*>(out)[c * CPL + j] = v[j];
+                        else reinterpret_cast<uint16_t*>(out)[c * CPL + j] = (uint16_t)v[j];
+                    }
+            }
+        }
+        __syncwarp();
+        return;
+    }
     if (valid_rows == 32) {
         const uint4* s4 = reinterpret_cast<const uint4*>(sv);
         uint4* o4 = reinterpret_cast<uint4*>(out);
@@ -345,6 +391,11 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
             }
         }
         game_unpack(g);
+        if (MODE == GM_GENERIC && p.tiles && !expand) {   // the planes are updated in place in HBM (same tile-of-32 layout, stride 32)
+            uint32_t* tp = p.tiles + (size_t)(gi >> 5) * (2 * TILE_PLANES * G::SW * 32) + (gi & 31);
+            g.b[0].tiles = tp;
+            g.b[1].tiles = tp + TILE_PLANES * G::SW * 32;
+        }
         const int flags_before = g.p[0].flags | g.p[1].flags;
         if (flags & KF_RESET) game_reset(g, tb, p.seeds[i]);
         if (flags & KF_POKE_DEAD) {
@@ -475,10 +526,22 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
     const int warp_row0 = blockIdx.x * TPB + warp * 32;
     int valid_rows = total_rows - warp_row0;
     valid_rows = valid_rows < 0 ? 0 : (valid_rows > 32 ? 32 : valid_rows);
-    if (p.field && valid_rows > 0)
-        emit_fields<G>(s_bits, swap ? g.b[1] : g.b[0], swap ? g.b[0] : g.b[1], active, p.field + (size_t)warp_row0 * (size_t)(2 * L::HW), valid_rows, lane);
-    if (p.vec && valid_rows > 0)
-        emit_vecs(s_vec, g.p[0], g.p[1], swap, active, p.vec + (size_t)warp_row0 * (size_t)(2 * VEC_LEN), valid_rows, lane);
+    const Board<G, WS>& fb0 = swap ? g.b[1] : g.b[0];
+    const Board<G, WS>& fb1 = swap ? g.b[0] : g.b[1];
+    if (MODE != GM_GENERIC || p.obs_dtype == 0) {      // uint8: the reference's dtype; the only one the two hot variants carry
+        if (p.field && valid_rows > 0) emit_fields<G>(s_bits, fb0, fb1, active, p.field + (size_t)warp_row0 * (size_t)(2 * L::HW), valid_rows, lane);
+        if (p.vec && valid_rows > 0) emit_vecs(s_vec, g.p[0], g.p[1], swap, active, p.vec + (size_t)warp_row0 * (size_t)(2 * VEC_LEN), valid_rows, lane);
+    } else if (p.obs_dtype == 3) {                     // float
+        if (p.field && valid_rows > 0) emit_fields<G, 4>(s_bits, fb0, fb1, active, p.field + (size_t)warp_row0 * (size_t)(8 * L::HW), valid_rows, lane, 0x3F800000u);
+        if (p.vec && valid_rows > 0) emit_vecs<3>(s_vec, g.p[0], g.p[1], swap, active, p.vec + (size_t)warp_row0 * (size_t)(8 * VEC_LEN), valid_rows, lane);
+    } else {                                           // half / bfloat16
+        const uint32_t one = p.obs_dtype == 1 ? 0x3C00u : 0x3F80u;
+        if (p.field && valid_rows > 0) emit_fields<G, 2>(s_bits, fb0, fb1, active, p.field + (size_t)warp_row0 * (size_t)(4 * L::HW), valid_rows, lane, one);
+        if (p.vec && valid_rows > 0) {
+            if (p.obs_dtype == 1) emit_vecs<1>(s_vec, g.p[0], g.p[1], swap, active, p.vec + (size_t)warp_row0 * (size_t)(4 * VEC_LEN), valid_rows, lane);
+            else emit_vecs<2>(s_vec, g.p[0], g.p[1], swap, active, p.vec + (size_t)warp_row0 * (size_t)(4 * VEC_LEN), valid_rows, lane);
+        }
+    }
     // ---- episode statistics: one atomic per non-zero counter per warp, spread over slices
     if (p.stats && (flags & KF_STEP)) {
         int vals[STAT_WORDS] = {st_steps, st_done, st_w0, st_w1, st_both, st_lines, st_gq, st_rng};
@@ -942,6 +1005,19 @@ __global__ void scatter_game_kernel(uint4* state, int game, int nv, const uint4*
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v < nv) state[((size_t)(game >> 5) * nv + v) * 32 + (game & 31)] = in[v];
 }
+// one game's colour-plane words <-> contiguous buffer (tile-of-32 layout, see KParams::tiles); copy between two games
+__global__ void gather_tiles_kernel(const uint32_t* tiles, int game, int nw, uint32_t* out) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < nw) out[w] = tiles[((size_t)(game >> 5) * nw + w) * 32 + (game & 31)];
+}
+__global__ void scatter_tiles_kernel(uint32_t* tiles, int game, int nw, const uint32_t* in) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < nw) tiles[((size_t)(game >> 5) * nw + w) * 32 + (game & 31)] = in[w];
+}
+__global__ void copy_tiles_kernel(uint32_t* dst_tiles, int dst, const uint32_t* src_tiles, int src, int nw) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < nw) dst_tiles[((size_t)(dst >> 5) * nw + w) * 32 + (dst & 31)] = src_tiles ? src_tiles[((size_t)(src >> 5) * nw + w) * 32 + (src & 31)] : 0u;
+}
 // PythonHandle.copy()/set() of one game, possibly between two handles of the same field size
 __global__ void copy_game_kernel(uint4* dst_state, int dst, const uint4* src_state, int src, int nv) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -958,8 +1034,9 @@ struct GeomOps {
     cudaError_t (*launch_enum)(const EParams&, cudaStream_t);
     cudaError_t (*launch_unpack)(const uint32_t*, const int32_t*, const int32_t*, int, int, int, uint8_t*, uint8_t*, cudaStream_t);
     cudaError_t (*launch_init)(uint4*, int, cudaStream_t);
-    void (*decode)(const uint32_t* words, b2t_game_raw* out, uint8_t* field);          // host codec, b2t_raw.cuh
-    void (*encode)(uint32_t* words, const b2t_game_raw* in, const uint8_t* field);
+    void (*decode)(const uint32_t* words, b2t_game_raw* out, uint8_t* field, const uint32_t* planes);          // host codec, b2t_raw.cuh
+    void (*encode)(uint32_t* words, const b2t_game_raw* in, const uint8_t* field, uint32_t* planes);
+    int tile_words;               // colour-plane words per game: 2 * TILE_PLANES * SW
 };
 
 template <class G> struct Launch {
@@ -978,7 +1055,8 @@ template <class G> struct Launch {
     static cudaError_t game(const KParams& p, int rows, cudaStream_t s) {
         if (rows <= 0) return cudaSuccess;
         const dim3 grid((rows + TPB - 1) / TPB);
-        if ((p.flags & ~KF_FINALIZE) == KF_EXPAND) game_kernel<G, GM_EXPAND><<<grid, TPB, L::GAME_TOTAL, s>>>(p);
+        if (p.obs_dtype != 0 || (p.tiles && !(p.flags & KF_EXPAND))) game_kernel<G, GM_GENERIC><<<grid, TPB, L::GAME_TOTAL, s>>>(p);
+        else if ((p.flags & ~KF_FINALIZE) == KF_EXPAND) game_kernel<G, GM_EXPAND><<<grid, TPB, L::GAME_TOTAL, s>>>(p);
         else if ((p.flags & ~KF_FINALIZE) == (KF_STEP | KF_STORE)) game_kernel<G, GM_STEP><<<grid, TPB, L::GAME_TOTAL, s>>>(p);
         else game_kernel<G, GM_GENERIC><<<grid, TPB, L::GAME_TOTAL, s>>>(p);
         return cudaGetLastError();
@@ -1001,7 +1079,7 @@ template <class G> struct Launch {
     }
     static const GeomOps* ops() {
         static const GeomOps o = {G::H, G::W, G::NV, G::KMAX, G::KEYW, G::LMAX, L::GAME_TOTAL, EnumCfg<G>::SMEM,
-                                  &prepare, &game, &enumerate, &unpack, &init, &decode_game<G>, &encode_game<G>};
+                                  &prepare, &game, &enumerate, &unpack, &init, &decode_game<G>, &encode_game<G>, 2 * TILE_PLANES * G::SW};
         return &o;
     }
 };

@@ -37,7 +37,8 @@ template <class G> struct HostGame {   // a Game<G,1> bound to plain host arrays
     }
 };
 
-template <class G> void decode_game(const uint32_t* words, b2t_game_raw* out, uint8_t* field) {
+// planes: the game's 2 x TILE_PLANES x SW colour-plane words (b2t_config.flags & B2T_FLAG_TILES) or NULL
+template <class G> void decode_game(const uint32_t* words, b2t_game_raw* out, uint8_t* field, const uint32_t* planes) {
     HostGame<G> hg;
     hg.load(words);
     PieceTables pt;
@@ -69,12 +70,17 @@ template <class G> void decode_game(const uint32_t* words, b2t_game_raw* out, ui
         r.piece_draws = (int32_t)s.piece_ctr; r.hole_draws = (int32_t)s.hole_ctr;
         out->overflow |= (int32_t)s.flags;
         if (field)
-            for (int c = 0; c < G::H * G::W; c++) field[p * G::H * G::W + c] = (uint8_t)((hg.g.b[p].sw(c >> 5) >> (c & 31)) & 1u);
+            for (int c = 0; c < G::H * G::W; c++) {
+                uint32_t v = (hg.g.b[p].sw(c >> 5) >> (c & 31)) & 1u;
+                if (v && planes)      // raw cell value 1..8 (gameField.cpp:105-110, gamePlay.cpp:202)
+                    for (int k = 0; k < TILE_PLANES; k++) v += ((planes[(p * TILE_PLANES + k) * G::SW + (c >> 5)] >> (c & 31)) & 1u) << k;
+                field[p * G::H * G::W + c] = (uint8_t)v;
+            }
     }
 }
 
 // words: the game's current packed state (boards are kept when field == NULL), rewritten in place
-template <class G> void encode_game(uint32_t* words, const b2t_game_raw* in, const uint8_t* field) {
+template <class G> void encode_game(uint32_t* words, const b2t_game_raw* in, const uint8_t* field, uint32_t* planes) {
     typedef typename G::col_t col_t;
     HostGame<G> hg;
     hg.load(words);
@@ -100,12 +106,17 @@ template <class G> void encode_game(uint32_t* words, const b2t_game_raw* in, con
         s.gq_n = (uint32_t)n;
         if (field) {
             board_clear<G, 1>(hg.g.b[p]);
+            if (planes)
+                for (int w = 0; w < TILE_PLANES * G::SW; w++) planes[p * TILE_PLANES * G::SW + w] = 0u;
             for (int y = 0; y < G::H; y++)
                 for (int x = 0; x < G::W; x++)
-                    if (field[(p * G::H + y) * G::W + x]) {
+                    if (const uint32_t v = field[(p * G::H + y) * G::W + x]) {
                         hg.g.b[p].col(x) |= (col_t)(G::one() << (y + G::YB));
                         const int bit = y * G::W + x;
                         hg.g.b[p].sw(bit >> 5) |= 1u << (bit & 31);
+                        if (planes)
+                            for (int k = 0; k < TILE_PLANES; k++)
+                                if ((((v > 8u ? 8u : v) - 1u) >> k) & 1u) planes[(p * TILE_PLANES + k) * G::SW + (bit >> 5)] |= 1u << (bit & 31);
                     }
         }
     }

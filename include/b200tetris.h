@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2T_ABI_VERSION 1
+#define B2T_ABI_VERSION 2
 #define B2T_VEC_LEN 19  /* x,y,incoming_lines,combo_time,combo_count,nextpiece[7],piece[7]  (state_processors.py:33-41) */
 #define B2T_SNAPSHOT_SLOTS 4
 
@@ -49,8 +49,14 @@ typedef struct {
     int32_t piece_stream_len;    /* draws tabulated per seed (0 = default 4096); a game drawing more raises a flag */
     int32_t hole_stream_len;     /* garbage holes tabulated per seed (0 = default 512) */
     int32_t device;              /* CUDA device ordinal */
-    uint32_t flags;              /* reserved, 0 */
+    uint32_t flags;              /* B2T_FLAG_* */
 } b2t_config;
+
+/* Keep the raw cell values of PythonHandle.states[p].field (1..7 = piece.tile, 8 = garbage; gameField.cpp:105-110,
+ * gamePlay.cpp:202) as three extra bit planes per player, for the renderer (environment/env_utils/draw_tetris.py:80-101) and
+ * raw-field parity: b2t_get_game / b2t_set_game then exchange 0..8 instead of 0/1.  Off by default: nothing observable
+ * through state_dict needs it, it adds 6*ceil(H*W/32) words of HBM traffic per stepped game and steps run the generic kernel. */
+#define B2T_FLAG_TILES 1u
 
 typedef struct b2t_handle b2t_handle;
 
@@ -60,6 +66,7 @@ typedef struct {
     int32_t lmax;           /* capacity of a key sequence */
     int32_t state_bytes;    /* bytes of packed state per game in HBM */
     int32_t obs_bytes;      /* 2*(H*W + 19 + 1) */
+    int32_t tile_bytes;     /* bytes of colour planes per game (0 without B2T_FLAG_TILES) */
 } b2t_info;
 
 /* tetris_env.set_pieces + tetris_env.PythonHandle(n_players,[H,W]) x n_games (tetris_environment.py:34-39).
@@ -75,9 +82,11 @@ int b2t_reset(b2t_handle *h, const int32_t *d_game_idx, int32_t n, const uint32_
 
 /* Observation tensors written by step / observe / expand: the reference's state_dict for BOTH players
  * (state_processors.py:23-54; layout consumed by agents/agent_utils/state_unpack.py:88-105).  Any pointer may be NULL. */
+typedef enum { B2T_U8 = 0, B2T_F16 = 1, B2T_BF16 = 2, B2T_F32 = 3 } b2t_dtype;
+
 typedef struct {
-    uint8_t *d_field;      /* [rows, 2, H, W]  field>0 */
-    uint8_t *d_vec;        /* [rows, 2, 19]    x, y, incoming_lines, min(25000,combo_time+50)//100, combo_count, nextpiece 1-hot, piece 1-hot */
+    void *d_field;         /* [rows, 2, H, W]  field>0 */
+    void *d_vec;           /* [rows, 2, 19]    x, y, incoming_lines, min(25000,combo_time+50)//100, combo_count, nextpiece 1-hot, piece 1-hot */
     uint8_t *d_piece_idx;  /* [rows, 2] */
     int32_t *d_scalars;    /* [rows, 2, 8] raw State views (PythonHandle.h:54-82): x,y,inc_lines,combo_time,combo_count,nextpiece,reward,dead */
     /* Player order of axis 1 of d_field / d_vec / d_piece_idx.  0: player index (0, 1).  1: perspective order (me, opponent),
@@ -86,6 +95,10 @@ typedef struct {
      * b2t_observe.  d_scalars always stays in player-index order. */
     int32_t perspective;
     const uint8_t *d_me;   /* [rows], only read by b2t_observe when perspective == 1 */
+    /* Element type of d_field and d_vec (b2t_dtype).  B2T_U8 is the reference's state_dict dtype; B2T_F16 / B2T_BF16 / B2T_F32
+     * write the same values (exactly representable: 0/1 cells, integers <= 255) as the floating type the consumer's network
+     * takes, so no conversion pass re-reads the tensors (state_unpack.py:88-105 casts them on the host in the reference). */
+    int32_t dtype;
 } b2t_obs;
 
 /* tetris_environment.perform_action for n games at once (tetris_environment.py:102-116; vector :79-86):
@@ -195,7 +208,7 @@ typedef struct {
     b2t_player_raw player[2];
 } b2t_game_raw;
 
-/* h_field: optional [2, H, W] bytes, the players' fields (non-zero = occupied).  b2t_set_game with h_field == NULL keeps the
+/* h_field: optional [2, H, W] bytes, the players' fields (non-zero = occupied; the raw values 1..8 with B2T_FLAG_TILES).  b2t_set_game with h_field == NULL keeps the
  * boards.  `piece` is output only (the piece is set through piece_kind / rotation).  Both synchronise. */
 int b2t_get_game(b2t_handle *h, int32_t game, b2t_game_raw *out, uint8_t *h_field);
 int b2t_set_game(b2t_handle *h, int32_t game, const b2t_game_raw *in, const uint8_t *h_field);

@@ -14,9 +14,9 @@ import pyhostsim  # noqa: E402
 
 
 class HostSimEngine:
-    def __init__(self, n_games, height, width, pieces, n_players=2, bar_null_moves=True, time_ms_per_action=400, device=0):
+    def __init__(self, n_games, height, width, pieces, n_players=2, bar_null_moves=True, time_ms_per_action=400, device=0, tiles=False):
         assert n_players == 2 and bar_null_moves
-        self.v = pyhostsim.HostSimVector(n_games, height, width, pieces)
+        self.v = pyhostsim.HostSimVector(n_games, height, width, pieces, tiles=tiles)
         self.n, self.H, self.W = n_games, height, width
         self.kmax, self.lmax = (256, 128) if width > 10 else (96, 64)
         self.default_ms = time_ms_per_action
@@ -58,3 +58,4 @@ def uninstall():
     tetris_env._engine_factory = Engine
     tetris_env._arenas.clear()
     tetris_env.set_arena_slots(4096)
+    tetris_env.set_tile_colours(False)

@@ -36,6 +36,8 @@ struct HSBase {
     virtual void copy_game(int dst, HSBase* from, int src) = 0;
     virtual void words_of(int game, uint32_t* out) = 0;
     virtual int nwords() = 0;
+    virtual void enable_tiles() = 0;
+    virtual uint32_t* planes_of(int game) = 0;
 };
 
 template <int KW> struct ListSink {
@@ -76,6 +78,10 @@ template <int H, int W> struct HS : HSBase {
     col_t cols[2][G::NCOL];
     uint32_t stream[2][G::SW];
     uint32_t gqw[2][GQ_WORDS];
+    std::vector<uint32_t> tiles;   // optional colour planes [n][2][TILE_PLANES][SW] (B2T_FLAG_TILES of the product)
+    static constexpr int TW = 2 * TILE_PLANES * G::SW;
+    void enable_tiles() override { tiles.assign((size_t)n * TW, 0u); }
+    uint32_t* planes_of(int gi) override { return tiles.empty() ? nullptr : tiles.data() + (size_t)gi * TW; }
 
     HS(int n_, const uint8_t* map_, uint32_t plen, uint32_t hlen) : n(n_), piece_len(plen), hole_len(hlen) {
         memcpy(map, map_, 7);
@@ -107,6 +113,7 @@ template <int H, int W> struct HS : HSBase {
         row_ready[s16] = 1;
     }
     void load(Game<G, 1>& g, int gi) {
+        for (int p = 0; p < 2; p++) g.b[p].tiles = tiles.empty() ? nullptr : planes_of(gi) + p * TILE_PLANES * G::SW;
         for (int v = 0; v < G::NV; v++)
             for (int k = 0; k < 4; k++) game_put_word(g, 4 * v + k, state[state_index<G>(gi, v) * 4 + k]);
         game_unpack(g);
@@ -256,12 +263,12 @@ template <int H, int W> struct HS : HSBase {
     void get_game(int gi, b2t_game_raw* out, uint8_t* field) override {   // the product's host codec (b2t_raw.cuh) on this store
         uint32_t w[4 * G::NV];
         words_of(gi, w);
-        decode_game<G>(w, out, field);
+        decode_game<G>(w, out, field, planes_of(gi));
     }
     void set_game(int gi, const b2t_game_raw* in, const uint8_t* field) override {
         uint32_t w[4 * G::NV];
         words_of(gi, w);
-        encode_game<G>(w, in, field);
+        encode_game<G>(w, in, field, field ? planes_of(gi) : nullptr);
         put_words(gi, w);
         ensure_row((uint32_t)in->seed16 & 0xFFFF);
     }
@@ -269,11 +276,15 @@ template <int H, int W> struct HS : HSBase {
         uint32_t w[4 * G::NV];
         from->words_of(src, w);
         put_words(dst, w);
+        if (uint32_t* d = planes_of(dst)) {
+            const uint32_t* sp = from->planes_of(src);
+            for (int k = 0; k < TW; k++) d[k] = sp ? sp[k] : 0u;
+        }
         ensure_row(seed_of(w));
     }
     uint32_t seed_of(const uint32_t* w) {
         b2t_game_raw r;
-        decode_game<G>(w, &r, nullptr);
+        decode_game<G>(w, &r, nullptr, nullptr);
         return (uint32_t)r.seed16 & 0xFFFF;
     }
     int flags(int gi) override {
@@ -310,5 +321,6 @@ int hs_expand(void* h, const int32_t* idx, int n, const uint8_t* player, int bar
 int hs_flags(void* h, int game) { return ((HSBase*)h)->flags(game); }
 void hs_get_game(void* h, int game, b2t_game_raw* out, uint8_t* field) { ((HSBase*)h)->get_game(game, out, field); }
 void hs_set_game(void* h, int game, const b2t_game_raw* in, const uint8_t* field) { ((HSBase*)h)->set_game(game, in, field); }
+void hs_enable_tiles(void* h) { ((HSBase*)h)->enable_tiles(); }
 void hs_copy_game(void* to, int dst, void* from, int src) { ((HSBase*)to)->copy_game(dst, (HSBase*)from, src); }
 }

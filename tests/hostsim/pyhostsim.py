@@ -40,6 +40,7 @@ def lib():
         L.hs_get_game.argtypes = [vp, i32, vp, u8p]
         L.hs_set_game.argtypes = [vp, i32, vp, u8p]
         L.hs_copy_game.argtypes = [vp, i32, vp, i32]
+        L.hs_enable_tiles.argtypes = [vp]
         L.hs_flags.restype = i32
         L.hs_flags.argtypes = [vp, i32]
         _lib = L
@@ -51,11 +52,13 @@ def _p(a, t):
 
 
 class HostSimVector:
-    def __init__(self, n_games, height=22, width=10, pieces=(0, 1, 2, 3, 4, 5, 6), piece_len=1024, hole_len=256):
+    def __init__(self, n_games, height=22, width=10, pieces=(0, 1, 2, 3, 4, 5, 6), piece_len=1024, hole_len=256, tiles=False):
         self.n, self.H, self.W, self.P = n_games, height, width, 2
         self.map = np.array((list(pieces) * 7)[:7], np.uint8)
         self.h = lib().hs_create(n_games, height, width, _p(self.map, C.c_uint8), piece_len, hole_len)
         assert self.h, "geometry %dx%d not in b2t_geoms.h" % (height, width)
+        if tiles:
+            lib().hs_enable_tiles(self.h)
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -53,7 +53,7 @@ CASES = [
 ]
 
 
-def run_case(module, kind, H, W, pieces, n, steps, solo):
+def run_case(module, kind, H, W, pieces, n, steps, solo, tiles=False):
     kmax, lmax = (256, 128) if W > 10 else (96, 64)
     lead = pyoracle.OracleVector(n, H, W, pieces)
     fac = FacadeVector(n, H, W, pieces, module)
@@ -64,10 +64,12 @@ def run_case(module, kind, H, W, pieces, n, steps, solo):
         if t == 0:
             a[..., -2:] = 0; b[..., -2:] = 0
         harness.assert_same("hidden", t, a, b)
-        g = lead.raw()[1]
+        f, g = lead.raw()[:2]
         for i in range(n):
             for p in range(2):
                 assert np.array_equal(g[i, p], np.array(other.h[i].states[p].piece)), ("piece grid", t, i, p)
+                if tiles:      # raw cell values 1..8 like the reference's states[p].field
+                    assert np.array_equal(f[i, p], np.array(other.h[i].states[p].field)), ("raw field", t, i, p)
     return harness.rollout_pair(lead, fac, steps, harness.Policy(kind, kmax=kmax, lmax=lmax, solo_period=solo), on_step=on_step)
 
 
@@ -193,6 +195,16 @@ def test_facade_semantics_cpu(cpu_facade):
     semantics(cpu_facade)
 
 
+@pytest.mark.parametrize("H,W,pieces,n,steps", [(22, 10, (0, 1, 2, 3, 4, 5, 6), 4, 300), (40, 20, (0, 1, 2, 3, 4, 5, 6), 2, 120), (16, 8, (0, 6), 3, 200)])
+def test_facade_tile_colours_cpu(cpu_facade, H, W, pieces, n, steps):
+    """set_tile_colours(True): states[p].field carries the reference's raw values (1..7 piece.tile, 8 garbage), incl. the
+    columns-0..9 garbage quirk at W != 10 (gamePlay.cpp:202) and the overwrite of a piece that dies on spawn."""
+    cpu_facade.set_tile_colours(True)
+    cpu_facade.set_pieces((list(pieces) * 7)[:7])
+    st = run_case(cpu_facade, "greedy", H, W, pieces, n, steps, 0, tiles=True)
+    assert st["garbage"] > 0 and st["lines"] > 0
+
+
 # ---- the reference's own front-end, unmodified, on both backends
 REF = refdrive.REFERENCE_TREE
 
@@ -302,6 +314,7 @@ def gpu_facade():
     yield tetris_env
     tetris_env._arenas.clear()
     tetris_env.set_arena_slots(4096)
+    tetris_env.set_tile_colours(False)
 
 
 @pytest.mark.gpu
@@ -315,3 +328,12 @@ def test_facade_matches_oracle_gpu(gpu_facade, kind, H, W, pieces, n, steps, sol
 @pytest.mark.gpu
 def test_facade_semantics_gpu(gpu_facade):
     semantics(gpu_facade)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,W,pieces,n,steps", [(22, 10, (0, 1, 2, 3, 4, 5, 6), 4, 300), (40, 20, (0, 1, 2, 3, 4, 5, 6), 2, 120), (16, 8, (0, 6), 3, 200)])
+def test_facade_tile_colours_gpu(gpu_facade, H, W, pieces, n, steps):
+    gpu_facade.set_tile_colours(True)
+    gpu_facade.set_pieces((list(pieces) * 7)[:7])
+    st = run_case(gpu_facade, "greedy", H, W, pieces, n, steps, 0, tiles=True)
+    assert st["garbage"] > 0 and st["lines"] > 0

@@ -490,3 +490,111 @@ def test_edge_cases_through_the_abi():
         b = v.enumerate(np.zeros(3, np.uint8), kmax=256, lmax=v.e.lmax)
         for x, y in zip(a[:3], b[:3]):
             assert np.array_equal(x, y)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,W,pieces", [(22, 10, ALL7), (12, 5, (4,)), (40, 20, ALL7)])
+def test_network_dtypes_equal_uint8_observations(H, W, pieces):
+    """b2t_obs.dtype: field / vec written directly as half, bfloat16 or float — by step, observe and expand, in
+    both player orders, for full and ragged last warps — hold exactly the uint8 values (cells 0/1, integers <= 255)."""
+    import torch
+    from b200tetris import Engine
+    dev = torch.device("cuda:0")
+    n = 1000 + 37                                   # not a multiple of 32: the last warp is ragged
+    e = Engine(n, H, W, pieces)
+    gids = np.arange(n)
+    e.reset_dev(torch.from_numpy(harness.seeds_for(gids, np.zeros(n, int)).astype(np.int64)).to(dev).to(torch.int32))
+    pol = harness.Policy("sventon", lmax=16)
+
+    def tensors(rows, dt):
+        return (torch.full((rows, 2, H, W), 7, dtype=dt, device=dev), torch.full((rows, 2, 19), 7, dtype=dt, device=dev))
+
+    class L:                                       # the sventon policy only needs the width
+        pass
+    L.W = W
+    for t in range(12):
+        player = ((gids + t) & 1).astype(np.uint8)
+        keys, klen, _ = pol.choose(L, t, gids, player)
+        pl = torch.from_numpy(player).to(dev)
+        f8, v8 = tensors(n, torch.uint8)
+        e.step_dev(pl, torch.from_numpy(keys).to(dev), torch.from_numpy(klen).to(dev), field=f8, vec=v8, perspective=bool(t & 2))
+        for dt in (torch.float16, torch.bfloat16, torch.float32):
+            f, v = tensors(n, dt)
+            if t & 2:
+                e.observe_dev(field=f, vec=v, me=pl)
+            else:
+                e.observe_dev(field=f, vec=v)
+            torch.cuda.synchronize()
+            assert torch.equal(f.to(torch.float32), f8.to(torch.float32)), (t, dt)
+            assert torch.equal(v.to(torch.float32), v8.to(torch.float32)), (t, dt)
+            idx = torch.arange(5, n, 3, device=dev, dtype=torch.int32)      # a subset: 345 rows
+            f, v = tensors(idx.numel(), dt)
+            e.observe_dev(idx=idx, field=f, vec=v)
+            fs, vs = tensors(idx.numel(), torch.uint8)
+            e.observe_dev(idx=idx, field=fs, vec=vs)
+            torch.cuda.synchronize()
+            assert torch.equal(f.to(torch.float32), fs.to(torch.float32)) and torch.equal(v.to(torch.float32), vs.to(torch.float32))
+    # the world model, and a step, writing the network's dtype directly
+    K = torch.empty(n, dtype=torch.int32, device=dev); offs = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    cap = n * e.kmax
+    pl = torch.from_numpy((gids & 1).astype(np.uint8)).to(dev)
+    f8, v8 = tensors(cap, torch.uint8)
+    e.expand_dev(pl, K, offs, cap, field=f8, vec=v8, perspective=True)
+    total = int(offs[-1].item())
+    for dt in (torch.bfloat16, torch.float32):
+        f, v = tensors(cap, dt)
+        e.expand_dev(pl, K, offs, cap, field=f, vec=v, perspective=True)
+        torch.cuda.synchronize()
+        assert torch.equal(f[:total].to(torch.float32), f8[:total].to(torch.float32)) and torch.equal(v[:total].to(torch.float32), v8[:total].to(torch.float32))
+        assert bool((f[total:] == 7).all()) and bool((v[total:] == 7).all())     # rows past the total are not touched
+    e.snapshot(0)
+    sel = (torch.arange(n, device=dev, dtype=torch.int32) * 7) % K
+    e.step_dev(pl, placement=sel, field=f8[:n], vec=v8[:n])
+    e.restore(0)
+    fh, vh = tensors(n, torch.float16)
+    e.step_dev(pl, placement=sel, field=fh, vec=vh)
+    torch.cuda.synchronize()
+    assert torch.equal(fh.to(torch.float32), f8[:n].to(torch.float32)) and torch.equal(vh.to(torch.float32), v8[:n].to(torch.float32))
+    with pytest.raises(ValueError):
+        e.observe_dev(field=fh, vec=v8[:n])
+    e.close()
+
+
+@pytest.mark.gpu
+def test_tile_colour_planes():
+    """B2T_FLAG_TILES: raw cell values 1..8 of states[p].field after every step vs the oracle (fused reset, garbage,
+    line clears), through snapshot / restore and b2t_copy_game, with every other observable identical to an engine without planes."""
+    from b200tetris import Engine
+    n = 96
+    o = pyoracle.OracleVector(n)
+    e = Engine(n, tiles=True)
+    plain = B200Vector(n)
+    assert e.state_bytes == plain.e.state_bytes
+
+    class V(B200Vector):
+        def __init__(self, eng):
+            self.n, self.H, self.W, self.P, self.bar_null, self.e = eng.n, eng.H, eng.W, 2, True, eng
+    v = V(e)
+    snap = {}
+
+    def on_step(t, player, keys, klen, rb, fb, enum, other):
+        if t % 25 == 0:
+            f = o.raw()[0]
+            for i in range(0, n, 7):
+                assert np.array_equal(e.get_game(i)[1], f[i]), (t, i)
+        if t == 120:
+            e.snapshot(1)
+            snap["f"] = o.raw()[0].copy()
+    st = harness.rollout_pair(o, v, 260, harness.Policy("greedy", kmax=96, lmax=64), on_step=on_step)
+    assert st["garbage"] > 0 and st["lines"] > 0 and st["dones"] > 0
+    f = o.raw()[0]
+    e.copy_game(3, e, 10)
+    assert np.array_equal(e.get_game(3)[1], f[10])
+    raw, fld = e.get_game(5)
+    fld[0, 21, :] = [1, 2, 3, 4, 5, 6, 7, 8, 0, 3]
+    e.set_game(5, raw, fld)
+    assert np.array_equal(e.get_game(5)[1], fld)
+    e.restore(1)
+    for i in range(0, n, 5):
+        assert np.array_equal(e.get_game(i)[1], snap["f"][i]), i
+    e.close()
