@@ -504,7 +504,7 @@ def test_network_dtypes_equal_uint8_observations(H, W, pieces):
     e = Engine(n, H, W, pieces)
     gids = np.arange(n)
     e.reset_dev(torch.from_numpy(harness.seeds_for(gids, np.zeros(n, int)).astype(np.int64)).to(dev).to(torch.int32))
-    pol = harness.Policy("sventon", lmax=16)
+    pol = harness.Policy("sventon", lmax=32)
 
     def tensors(rows, dt):
         return (torch.full((rows, 2, H, W), 7, dtype=dt, device=dev), torch.full((rows, 2, 19), 7, dtype=dt, device=dev))
@@ -565,11 +565,10 @@ def test_tile_colour_planes():
     """B2T_FLAG_TILES: raw cell values 1..8 of states[p].field after every step vs the oracle (fused reset, garbage,
     line clears), through snapshot / restore and b2t_copy_game, with every other observable identical to an engine without planes."""
     from b200tetris import Engine
+    from b200vec import B200Vector
     n = 96
     o = pyoracle.OracleVector(n)
     e = Engine(n, tiles=True)
-    plain = B200Vector(n)
-    assert e.state_bytes == plain.e.state_bytes
 
     class V(B200Vector):
         def __init__(self, eng):
