@@ -2,6 +2,7 @@
 // the *_host entry points.  No game logic lives here and there is no CPU path: every call ends in a kernel launch.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -71,6 +72,7 @@ struct b2t_handle {
     size_t tile_words_total = 0;
     DevTabs tabs;
     Arena in, out;
+    cudaStream_t pipe[2] = {nullptr, nullptr};   // b2t_step_host slices large batches over two streams (copies overlap the kernel)
     bool enumerated = false;
     std::string err;
 };
@@ -87,6 +89,8 @@ static int fail(b2t_handle* h, int code, const char* fmt, const char* a = "", lo
         if (e_ != cudaSuccess) return fail(h, B2T_ERR_CUDA, "CUDA error: %s (line %lld)", cudaGetErrorString(e_), __LINE__); \
     } while (0)
 
+constexpr int PIPE_MIN_ROWS = 1 << 16;   // b2t_step_host: batches at least this large are sliced over two streams
+constexpr int PIPE_SLICES = 2;       // measured on the B200 box: H2D (25-38 GB/s pinned) bounds the call; 2 slices 0.68 ms, 1: 0.74, 8: 0.92 (profiles/e2e_probe.py)
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 extern "C" {
@@ -103,6 +107,7 @@ int b2t_destroy(b2t_handle* h) {
     cudaFree(h->plc); cudaFree(h->kcache); cudaFree(h->scan_sums); cudaFree(h->d_total); cudaFree(h->row_meta);
     cudaFree(h->piece_tab); cudaFree(h->hole_tab); cudaFree(h->powtab); cudaFree(h->stats); cudaFree(h->xfer);
     h->in.release(); h->out.release();
+    for (auto st : h->pipe) if (st) cudaStreamDestroy(st);
     delete h;
     return B2T_OK;
 }
@@ -223,15 +228,17 @@ int b2t_reset(b2t_handle* h, const int32_t* d_idx, int32_t n, const uint32_t* d_
     return B2T_OK;
 }
 
-int b2t_step(b2t_handle* h, const b2t_step_args* a, void* stream) {
+static int step_launch(b2t_handle* h, const b2t_step_args* a, int32_t game0, void* stream);
+int b2t_step(b2t_handle* h, const b2t_step_args* a, void* stream) { return step_launch(h, a, 0, stream); }
+static int step_launch(b2t_handle* h, const b2t_step_args* a, int32_t game0, void* stream) {
     if (!h || !a) return B2T_ERR_ARG;
-    if (a->n < 0 || a->n > h->cfg.n_games || !a->d_player) return fail(h, B2T_ERR_ARG, "b2t_step: bad n or NULL d_player%s");
+    if (a->n < 0 || game0 < 0 || a->n + game0 > h->cfg.n_games || !a->d_player) return fail(h, B2T_ERR_ARG, "b2t_step: bad n or NULL d_player%s");
     if (!a->d_placement && (!a->d_keys || !a->d_key_len || a->lmax < 1)) return fail(h, B2T_ERR_ARG, "b2t_step: need d_placement or d_keys+d_key_len+lmax%s");
     if (a->d_placement && !h->enumerated) return fail(h, B2T_ERR_STATE, "b2t_step: d_placement needs a prior b2t_enumerate/b2t_expand%s");
     if (int r = check_obs(h, a->obs)) return r;
     CK(cudaSetDevice(h->cfg.device));
     KParams p; base_params(h, p);
-    p.idx = a->d_game_idx; p.n = a->n; p.player = a->d_player;
+    p.idx = a->d_game_idx; p.game0 = game0; p.n = a->n; p.player = a->d_player;
     p.keys = a->d_keys; p.key_len = a->d_key_len; p.lmax = a->lmax; p.placement = a->d_placement;
     p.flags = KF_STEP | KF_STORE | (a->finalize ? KF_FINALIZE : 0u);
     if (a->time_ms > 0) p.elapsed = a->time_ms;
@@ -522,8 +529,68 @@ int b2t_step_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint8_t*
     idx.src = h_idx; idx.bytes = N * 4; pl.src = h_player; pl.bytes = N;
     keys.src = h_keys; keys.bytes = N * (size_t)(lmax > 0 ? lmax : 0); klen.src = h_key_len; klen.bytes = N;
     plc.src = h_placement; plc.bytes = N * 4; rs.src = h_reset_seeds; rs.bytes = N * 4;
-    if (int r = stage_in(h, {&idx, &pl, &keys, &klen, &plc, &rs}, 0)) return r;
     Out rew, done, lines, field, vec, pidx, scal;
+    rew.dst = h_reward; rew.bytes = N; done.dst = h_done; done.bytes = N; lines.dst = h_lines; lines.bytes = 2 * N;
+    field.dst = h_field; field.bytes = 2 * HW * N; vec.dst = h_vec; vec.bytes = 2 * B2T_VEC_LEN * N;
+    pidx.dst = h_piece_idx; pidx.bytes = 2 * N; scal.dst = h_scalars; scal.bytes = 64 * N;
+    if (n >= PIPE_MIN_ROWS) {
+        // Large batch: slices of the rows go down, through the kernel and back up on two streams, so the PCIe copies of one
+        // slice overlap the kernel of another (a step of 2^20 games is 23 MB in, 0.25 ms of kernel, 4 MB out).
+        std::vector<In*> ins = {&idx, &pl, &keys, &klen, &plc, &rs};
+        std::vector<Out*> outs = {&rew, &done, &lines, &field, &vec, &pidx, &scal};
+        const size_t in_row[6] = {4, 1, (size_t)(lmax > 0 ? lmax : 0), 1, 4, 4};
+        const size_t out_row[7] = {1, 1, 2, 2 * HW, 2 * B2T_VEC_LEN, 2, 64};
+        size_t total = 0;
+        for (auto i : ins) if (i->src) total += (i->bytes + 255) & ~(size_t)255;
+        CK(h->in.reserve(total + 256));
+        for (auto i : ins) if (i->src) i->off = h->in.take(i->bytes ? i->bytes : 1);
+        if (int r = plan_out(h, outs)) return r;
+        for (auto& st : h->pipe) if (!st) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CK(cudaStreamSynchronize(0));               // earlier work of this handle went to the default stream
+        bool pinned_in[6], pinned_out[7];
+        for (int k = 0; k < 6; k++) pinned_in[k] = ins[k]->src && is_pinned(ins[k]->src);
+        for (int k = 0; k < 7; k++) pinned_out[k] = outs[k]->dst && is_pinned(outs[k]->dst);
+        static const int slices_env = getenv("B2T_PIPE_SLICES") ? atoi(getenv("B2T_PIPE_SLICES")) : 0;   // tuning knob
+        const int slices = slices_env > 0 ? slices_env : PIPE_SLICES;
+        const int per = (((n + slices - 1) / slices) + 1023) & ~1023;      // slice starts stay 16-byte aligned in every array
+        for (int c = 0, lo = 0; lo < n; c++, lo += per) {
+            const int cnt = (n - lo) < per ? (n - lo) : per;
+            cudaStream_t st = h->pipe[c & 1];
+            for (int k = 0; k < 6; k++) {
+                In* i = ins[k];
+                if (!i->src || !in_row[k]) continue;
+                const size_t o = (size_t)lo * in_row[k], b = (size_t)cnt * in_row[k];
+                const unsigned char* from = (const unsigned char*)i->src + o;
+                if (!pinned_in[k]) { memcpy(h->in.h + i->off + o, from, b); from = h->in.h + i->off + o; }
+                CK(cudaMemcpyAsync(h->in.d + i->off + o, from, b, cudaMemcpyHostToDevice, st));
+            }
+            b2t_step_args a;
+            memset(&a, 0, sizeof a);
+            auto din = [&](const In& i, int k) -> const void* { return i.src ? h->in.d + i.off + (size_t)lo * in_row[k] : nullptr; };
+            auto dout = [&](const Out& o, int k) -> void* { return o.dst ? h->out.d + o.off + (size_t)lo * out_row[k] : nullptr; };
+            a.d_game_idx = (const int32_t*)din(idx, 0); a.n = cnt; a.d_player = (const uint8_t*)din(pl, 1);
+            a.d_keys = (const uint8_t*)din(keys, 2); a.d_key_len = (const uint8_t*)din(klen, 3); a.lmax = lmax;
+            a.d_placement = (const int32_t*)din(plc, 4); a.finalize = finalize; a.time_ms = time_ms;
+            a.d_reset_seeds = (const uint32_t*)din(rs, 5);
+            a.d_reward = (int8_t*)dout(rew, 0); a.d_done = (uint8_t*)dout(done, 1); a.d_lines = (uint8_t*)dout(lines, 2);
+            a.obs.d_field = dout(field, 3); a.obs.d_vec = dout(vec, 4);
+            a.obs.d_piece_idx = (uint8_t*)dout(pidx, 5); a.obs.d_scalars = (int32_t*)dout(scal, 6);
+            if (int r = step_launch(h, &a, h_idx ? 0 : lo, st)) return r;
+            for (int k = 0; k < 7; k++) {
+                Out* o = outs[k];
+                if (!o->dst) continue;
+                const size_t off = (size_t)lo * out_row[k], b = (size_t)cnt * out_row[k];
+                void* to = pinned_out[k] ? (unsigned char*)o->dst + off : h->out.h + o->off + off;
+                CK(cudaMemcpyAsync(to, h->out.d + o->off + off, b, cudaMemcpyDeviceToHost, st));
+            }
+        }
+        CK(cudaStreamSynchronize(h->pipe[0]));
+        CK(cudaStreamSynchronize(h->pipe[1]));
+        for (int k = 0; k < 7; k++)
+            if (outs[k]->dst && !pinned_out[k]) memcpy(outs[k]->dst, h->out.h + outs[k]->off, outs[k]->bytes);
+        return B2T_OK;
+    }
+    if (int r = stage_in(h, {&idx, &pl, &keys, &klen, &plc, &rs}, 0)) return r;
     rew.dst = h_reward; rew.bytes = N; done.dst = h_done; done.bytes = N; lines.dst = h_lines; lines.bytes = 2 * N;
     field.dst = h_field; field.bytes = 2 * HW * N; vec.dst = h_vec; vec.bytes = 2 * B2T_VEC_LEN * N;
     pidx.dst = h_piece_idx; pidx.bytes = 2 * N; scal.dst = h_scalars; scal.bytes = 64 * N;

@@ -48,6 +48,7 @@ struct KParams {
     uint32_t* tiles;              // optional colour planes [n_tiles][2*TILE_PLANES*SW][32] (B2T_FLAG_TILES), generic variant only
     int32_t n_games;
     const int32_t* idx;
+    int32_t game0;                // idx == NULL: row i is game game0 + i (a slice of a pipelined host call)
     int32_t n;
     uint32_t flags;
     const uint32_t* seeds;        // KF_RESET
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams 
             const int4 m = p.row_meta[row];
             i = m.x; gi = m.y; k = m.z; player = m.w; sel = k;
         } else {
-            gi = p.idx ? p.idx[i] : i;
+            gi = p.idx ? p.idx[i] : i + p.game0;
             if (stepping) {
                 player = p.player[i] ? 1 : 0;
                 if (p.placement) sel = p.placement[i]; else nkeys = p.key_len[i];
