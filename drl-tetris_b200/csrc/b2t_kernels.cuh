@@ -307,8 +307,10 @@ __device__ __forceinline__ uint32_t spread_nibbles(uint32_t x) {
 // MODE: 0 = every flag is read at run time (reset / observe / pokes / steps without write-back);  1 = expand and 2 = the plain
 // stored step are compiled with their flag set fixed, so the two hot variants carry no code for the others' paths.
 constexpr int GM_GENERIC = 0, GM_EXPAND = 1, GM_STEP = 2;
+// (expand is latency-bound: a fifth resident block — 96 registers, no spills — is 3.5 % faster; the stored step is HBM-bound and
+// loses 14 % to the same cap, measured)
 template <class G, int MODE>
-__global__ void __launch_bounds__(TPB, B2T_GAME_MINB) game_kernel(const KParams p) {
+__global__ void __launch_bounds__(TPB, MODE == GM_EXPAND ? B2T_GAME_MINB + 1 : B2T_GAME_MINB) game_kernel(const KParams p) {
     typedef typename G::col_t col_t;
     typedef SmemLayout<G> L;
     constexpr int KW = G::KEYW;
@@ -584,27 +586,35 @@ struct EParams {
 // combo's cavities by increasing height.
 constexpr int ETPB = 64;              // threads per block of the enumerate kernel (small: 65 536 boards must still fill 148 SMs)
 constexpr int EWARPS = ETPB / 32;
+#ifndef B2T_ENUM_BPW
+#define B2T_ENUM_BPW 32
+#endif
+// Boards per warp.  Phases 1 and 3 run one board per lane (lanes >= BPW idle); the pooled search of phase 2 always uses all 32
+// lanes on the warp's candidates.  Fewer boards per warp = more, shorter warps: the kernel is bound by the serial length of a
+// warp's work (65 536 boards are only 2048 warps at 32 per warp), not by issue slots.
+constexpr int BPW = B2T_ENUM_BPW;
+constexpr int ENB = EWARPS * BPW;     // boards per block = stride of every per-board array in shared memory
 
 template <class G> struct EnumCfg {
     static constexpr int CCAP = 32;                                  // candidate slots per thread between two pooled searches
     static constexpr int PER_COMBO = (G::H - 1) / 2;                 // resting heights differ by >= 2 and start at 2
     static constexpr int NCOMBO = 4 * G::W;
     static constexpr int ACAP = G::KMAX;                             // accepted finesse entries per board (cannot overflow before the list does)
-    static constexpr int RES = 192;                                  // pooled results buffered per warp between acceptances (smem: 7 blocks/SM)
+    static constexpr int RES = 192 * BPW / 32 < 64 ? 64 : 192 * BPW / 32;   // pooled results buffered per warp between acceptances
     static constexpr int PCAP = EnumGeo<G>::PCAP;
     static constexpr int RSW = 1 + (PCAP + 3) / 4;                   // result slot: header word + the raw search path
     static_assert(NCOMBO <= 128, "topmask is 128 bits");
     static_assert(PER_COMBO <= CCAP, "a single combo must fit the candidate slots");
-    static constexpr int O_CAND = G::NCOL * ETPB * (int)sizeof(typename G::col_t);
-    static constexpr int O_PC4 = O_CAND + CCAP * ETPB * 2;
-    static constexpr int O_RES = O_PC4 + ETPB * 16;
+    static constexpr int O_CAND = G::NCOL * ENB * (int)sizeof(typename G::col_t);
+    static constexpr int O_PC4 = O_CAND + CCAP * ENB * 2;
+    static constexpr int O_RES = O_PC4 + ENB * 16;
     static constexpr int O_INCL = O_RES + EWARPS * RES * RSW * 4;
     static constexpr int O_Q = O_INCL + EWARPS * 32 * 4;
     static constexpr int O_KIND = O_Q + EWARPS * 4 + ((EWARPS & 1) ? 4 : 0);
-    static constexpr int O_TAB = O_KIND + ETPB * 4;
+    static constexpr int O_TAB = O_KIND + ENB * 4;
     static constexpr int O_ACC = O_TAB + 128;
-    static constexpr int O_PBUF = O_ACC + ACAP * ETPB;
-    static constexpr int SMEM = O_PBUF + G::KEYW * ETPB * 4 + 16;   // O_PBUF: per-thread scratch for the sequence being accepted
+    static constexpr int O_PBUF = ((O_ACC + ACAP * ENB + 15) / 16) * 16;
+    static constexpr int SMEM = O_PBUF + G::KEYW * ENB * 4 + 16;   // O_PBUF: per-thread scratch for the sequence being accepted
 };
 
 struct NoSink {
@@ -635,19 +645,21 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
     uint16_t* s_tab = reinterpret_cast<uint16_t*>(smem + C::O_TAB);
     uint8_t* s_acc = smem + C::O_ACC;                                   // [ACAP][ETPB] combo of every accepted finesse entry
     uint32_t* s_seq = reinterpret_cast<uint32_t*>(smem + C::O_PBUF);    // [KW][ETPB] key string being accepted by this owner
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int i = blockIdx.x * ETPB + tid;
-    if (tid < 28) { s_tab[tid] = p.tabs.pcn[tid]; s_tab[32 + tid] = p.tabs.pcc[tid]; }
+    const int tid0 = threadIdx.x, lane = tid0 & 31, warp = tid0 >> 5;
+    const bool has = lane < BPW;                        // this lane carries a board
+    const int tid = warp * BPW + (has ? lane : 0);      // board slot in the block's shared arrays (idle lanes alias slot 0, read-only)
+    const int i = blockIdx.x * ENB + tid;
+    if (tid0 < 28) { s_tab[tid0] = p.tabs.pcn[tid0]; s_tab[32 + tid0] = p.tabs.pcc[tid0]; }
     Tabs tb;
     tb.pcn = s_tab; tb.pcc = s_tab + 32;
     tb.piece = p.tabs.piece; tb.hole = p.tabs.hole; tb.powtab = p.tabs.powtab;
     tb.piece_len = p.tabs.piece_len; tb.hole_len = p.tabs.hole_len; tb.spawn_rots = p.tabs.spawn_rots;
-    Board<G, ETPB> b;
+    Board<G, ENB> b;
     b.cols = s_cols + tid;
     b.stream = nullptr;
-    board_init_walls<G, ETPB>(b);
+    if (has) board_init_walls<G, ENB>(b);
     __syncthreads();
-    const bool active = i < p.n;
+    const bool active = has && i < p.n;
     int gi = 0, kind = 7, cur_rot = 0;
     if (active) {
         gi = p.idx ? p.idx[i] : i;
@@ -669,8 +681,7 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
         pcn4 |= (uint64_t)tb.pcn[kk * 4 + r] << (16 * r);
         pcc4 |= (uint64_t)tb.pcc[kk * 4 + r] << (16 * r);
     }
-    s_pc4[2 * tid] = pcn4; s_pc4[2 * tid + 1] = pcc4;
-    s_kind[tid] = kk;
+    if (has) { s_pc4[2 * tid] = pcn4; s_pc4[2 * tid + 1] = pcc4; s_kind[tid] = kk; }
     const int nrot = (kind > 6) ? 0 : (kind == 6) ? 1 : (kind == 4 || kind == 2 || kind == 3) ? 2 : 4;
     const int spawn = spawn_rot_of(tb, kk);
     const int off = p.bar_null ? 0 : 1;
@@ -678,7 +689,7 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
     uint64_t top_lo = 0, top_hi = 0;
     int nacc = 0, bad = 0;
     NoSink ns;
-    Enumerator<G, ETPB, KW, NoSink, 1> e(b, tb, kk, ns, nullptr);
+    Enumerator<G, ENB, KW, NoSink, 1> e(b, tb, kk, ns, nullptr);
     __syncwarp();
 
     int c_next = 0;
@@ -690,7 +701,7 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
             const int r0 = c & 3, xx = (c >> 2) - 1;
             if (r0 < nrot) {
                 const int r = (kind == 6) ? cur_rot : r0;
-                const col_t cm = collide_mask<G, ETPB>(b, xx, (uint32_t)(pcc4 >> (16 * r)) & 0xFFFFu);
+                const col_t cm = collide_mask<G, ENB>(b, xx, (uint32_t)(pcc4 >> (16 * r)) & 0xFFFFu);
                 if (!((cm >> G::YB) & 1)) {
                     if (c < 64) top_lo |= 1ull << c; else top_hi |= 1ull << (c - 64);
                     int yy = rest_from<G>(cm, 0) + 2;
@@ -699,7 +710,7 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
                         free_ &= (col_t)((G::one() << (G::H - 1 - yy)) - 1);
                         if (!free_) break;
                         const int rest = rest_from<G>(cm, yy + ctz(free_));
-                        if (ncand < C::CCAP) s_cand[ncand * ETPB + tid] = (uint16_t)((c << 8) | (r << 6) | rest);
+                        if (ncand < C::CCAP) s_cand[ncand * ENB + tid] = (uint16_t)((c << 8) | (r << 6) | rest);
                         else bad = 1;
                         ncand++;
                         yy = rest + 1;
@@ -738,9 +749,9 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
                             if (t <= 31 && s_incl[warp * 32 + t - 1] <= g) o = t;
                         }
                         const int o_excl = o ? s_incl[warp * 32 + o - 1] : 0;
-                        const int otid = warp * 32 + o;
-                        const uint32_t cd = s_cand[(g - o_excl) * ETPB + otid];
-                        Board<G, ETPB> ob;
+                        const int otid = warp * BPW + o;
+                        const uint32_t cd = s_cand[(g - o_excl) * ENB + otid];
+                        Board<G, ENB> ob;
                         ob.cols = s_cols + otid;
                         ob.stream = nullptr;
                         const int okind = s_kind[otid];
@@ -773,22 +784,22 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
                 const uint32_t* slot_in = s_res + (warp * C::RES + t) * C::RSW;
                 const uint32_t hd = slot_in[0];
                 // expand the recorded move into its forward key string (useFinesseMove, TestField.cpp:127-164)
-                uint32_t* rr = s_seq + tid;                     // word j at rr[j * ETPB]
-                WordWriter<KW, ETPB> w(rr);
-                Enumerator<G, ETPB, KW, NoSink, 1>::template write_finesse_raw<WordWriter<KW, ETPB>, 1>(
+                uint32_t* rr = s_seq + tid;                     // word j at rr[j * ENB]
+                WordWriter<KW, ENB> w(rr);
+                Enumerator<G, ENB, KW, NoSink, 1>::template write_finesse_raw<WordWriter<KW, ENB>, 1>(
                     w, reinterpret_cast<const uint8_t*>(slot_in + 1), (int)((hd >> 16) & 255u), (int)((hd >> 8) & 255u) - 8, (int)((hd >> 2) & 3u), spawn);
                 w.finish();
                 if (w.bad || (hd & 1u)) bad = 1;
-                const int cc = (int)(s_cand[(g0 + t - excl) * ETPB + tid] >> 8);
+                const int cc = (int)(s_cand[(g0 + t - excl) * ENB + tid] >> 8);
                 bool dup = false;
                 for (int f = 0; f < nacc && !dup; f++) {
-                    const int fc = s_acc[f * ETPB + tid];
+                    const int fc = s_acc[f * ENB + tid];
                     const int slot = off + rank128(top_lo, top_hi, fc + 1) + f;
                     if (slot < G::KMAX) {
                         const uint32_t* q = lst + (size_t)slot * KW;
                         bool eq = true;
 #pragma unroll
-                        for (int j = 0; j < KW; j++) eq = eq && (q[j] == rr[j * ETPB]);
+                        for (int j = 0; j < KW; j++) eq = eq && (q[j] == rr[j * ENB]);
                         dup = eq;
                     }
                 }
@@ -798,8 +809,8 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
                     uint4* dst = reinterpret_cast<uint4*>(lst + (size_t)slot * KW);
 #pragma unroll
                     for (int j = 0; j < KW / 4; j++)
-                        dst[j] = make_uint4(rr[(4 * j) * ETPB], rr[(4 * j + 1) * ETPB], rr[(4 * j + 2) * ETPB], rr[(4 * j + 3) * ETPB]);
-                    s_acc[nacc * ETPB + tid] = (uint8_t)cc;
+                        dst[j] = make_uint4(rr[(4 * j) * ENB], rr[(4 * j + 1) * ENB], rr[(4 * j + 2) * ENB], rr[(4 * j + 3) * ENB]);
+                    s_acc[nacc * ENB + tid] = (uint8_t)cc;
                 } else bad = 1;
                 nacc++;
             }
@@ -813,7 +824,7 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
         for (int c = 0; c < C::NCOMBO; c++) {
             const bool has = (c < 64) ? ((top_lo >> c) & 1ull) : ((top_hi >> (c - 64)) & 1ull);
             if (!has) continue;
-            while (f < nacc && s_acc[f * ETPB + tid] < c) f++;
+            while (f < nacc && s_acc[f * ENB + tid] < c) f++;
             const int slot = off + ntop + f;
             const int r = (kind == 6) ? cur_rot : (c & 3);
             const uint64_t t = top_drop_tokens((r - spawn) & 3, ((c >> 2) - 1) - G::SPAWN_X);
@@ -1064,7 +1075,7 @@ template <class G> struct Launch {
     }
     static cudaError_t enumerate(const EParams& p, cudaStream_t s) {
         if (p.n <= 0) return cudaSuccess;
-        enumerate_kernel<G><<<(p.n + ETPB - 1) / ETPB, ETPB, EnumCfg<G>::SMEM, s>>>(p);
+        enumerate_kernel<G><<<(p.n + ENB - 1) / ENB, ETPB, EnumCfg<G>::SMEM, s>>>(p);
         return cudaGetLastError();
     }
     static cudaError_t unpack(const uint32_t* plc, const int32_t* kc, const int32_t* idx, int n, int kmax, int lmax, uint8_t* keys,
