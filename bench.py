@@ -35,6 +35,13 @@ def board_bytes(mean_k):                         # 352 + 520*K per expanded boar
     return S_BYTES + 8 + mean_k * (OBS_BYTES + 32 + 8)
 
 
+def geom_bytes(h, w):
+    """SURVEY.md §8d for any field size: (OBS, S, bytes per env-step, bytes per expanded board as a function of mean K)"""
+    obs = 2 * (h * w + 19 + 1)
+    st = 2 * (h * ((w + 7) // 8) + 128)
+    return obs, st, 2 * st + obs + 37, (lambda k: st + 8 + k * (obs + 32 + 8))
+
+
 def splitmix64(*words):
     z = np.uint64(0x9E3779B97F4A7C15)
     with np.errstate(over="ignore"):
@@ -47,11 +54,11 @@ def splitmix64(*words):
     return acc
 
 
-def sventon_keys(gids, t, lmax=16):
+def sventon_keys(gids, t, lmax=16, width=W):
     """[8]*r + [2] + [3]*tr + [7], r in [0,4), tr in [0,W) from a counter hash of (global game id, step)."""
     h = splitmix64(7, gids, t)
     r = (h % np.uint64(4)).astype(np.int64)
-    tr = ((h >> np.uint64(8)) % np.uint64(W)).astype(np.int64)
+    tr = ((h >> np.uint64(8)) % np.uint64(width)).astype(np.int64)
     n = len(gids)
     col = np.arange(lmax)[None, :]
     keys = np.zeros((n, lmax), np.uint8)
@@ -188,6 +195,75 @@ def reference_leg(steps, per_proc_games=64, per_proc_steps=40):
             res = pool.map(_ref_worker, [(w, per_proc_games, per_proc_steps) for w in range(cores)])
             vals.append(sum(r[0] for r in res) / max(r[1] for r in res))
     return float(np.median(vals)), cores, "reference", "%d procs x %d games x %d steps of workload S, raw PythonHandle make_action+finish_action loop (no Python front-end, no state copies)" % (cores, per_proc_games, per_proc_steps)
+
+
+def c5_leg(torch, Engine, dev, local, rank, h, w, pieces, n, nb, peak, steps):
+    """BASELINE configs[4]: a custom field size / piece set at 2^18 games — the step kernel on workload S and the world model on
+    nb boards, each against the algorithmic bytes of ITS geometry."""
+    obs, st, step_b, board_b = geom_bytes(h, w)
+    gids = np.arange(n, dtype=np.int64) + rank * n
+    eng = Engine(n, h, w, pieces, device=local)
+    lmax = 16 if w <= 10 else 32
+    ring = []
+    for t in range(4):
+        k, ln = sventon_keys(gids, t, lmax=lmax, width=w)
+        ring.append((torch.from_numpy(k).to(dev), torch.from_numpy(ln).to(dev),
+                     torch.from_numpy((splitmix64(0xB200, gids, t + 1) & np.uint64(0xFFFF)).astype(np.int64)).to(dev).to(torch.int32),
+                     torch.from_numpy(((gids + t) & 1).astype(np.uint8)).to(dev)))
+    reward = torch.empty(n, dtype=torch.int8, device=dev); done = torch.empty(n, dtype=torch.uint8, device=dev)
+    field = torch.empty((n, 2, h, w), dtype=torch.uint8, device=dev); vec = torch.empty((n, 2, 19), dtype=torch.uint8, device=dev)
+    pidx = torch.empty((n, 2), dtype=torch.uint8, device=dev)
+    eng.reset_dev(torch.from_numpy((splitmix64(0xB200, gids, 0) & np.uint64(0xFFFF)).astype(np.int64)).to(dev).to(torch.int32))
+
+    def one(t):
+        k, ln, sd, pl = ring[t % 4]
+        eng.step_dev(pl, k, ln, reset_seeds=sd, reward=reward, done=done, field=field, vec=vec, piece_idx=pidx)
+    for t in range(4):
+        one(t)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for t in range(steps):
+        one(4 + t)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"game_size": [h, w], "pieces": list(pieces), "games_per_gpu": n, "env_steps_per_sec": n / (ms * 1e-3), "ms_per_step": ms,
+           "algorithmic_bytes_per_env_step": step_b, "roofline_frac": step_b * n / (ms * 1e-3) / 1e9 / peak}
+    # world model on the first nb games after a few plies of random placements
+    K = torch.empty(nb, dtype=torch.int32, device=dev); offs = torch.empty(nb + 1, dtype=torch.int32, device=dev)
+    idx = torch.arange(nb, device=dev, dtype=torch.int32)
+    gen = torch.Generator(device=dev); gen.manual_seed(77 + rank)
+    for t in range(12):
+        pl = ring[t & 1][3][:nb].contiguous()
+        eng.enumerate_dev(pl, K, idx=idx)
+        sel = (torch.randint(0, 1 << 30, (nb,), device=dev, generator=gen) % K.to(torch.int64)).to(torch.int32)
+        eng.step_dev(pl, idx=idx, placement=sel)
+    side = ring[0][3][:nb].contiguous()
+    eng.enumerate_dev(side, K, idx=idx)
+    torch.cuda.synchronize()
+    cap = int(K.sum().item()) + 1024
+    pf = torch.empty((cap, 2, h, w), dtype=torch.uint8, device=dev); pv = torch.empty((cap, 2, 19), dtype=torch.uint8, device=dev)
+    pp = torch.empty((cap, 2), dtype=torch.uint8, device=dev); pk = torch.empty((cap, eng.lmax), dtype=torch.uint8, device=dev)
+    pl_ = torch.empty(cap, dtype=torch.uint8, device=dev); pr = torch.empty(cap, dtype=torch.int8, device=dev); pd = torch.empty(cap, dtype=torch.uint8, device=dev)
+
+    def expand():
+        eng.expand_dev(side, K, offs, cap, idx=idx, keys=pk, key_len=pl_, reward=pr, done=pd, field=pf, vec=pv, piece_idx=pp)
+    for _ in range(2):
+        expand()
+    torch.cuda.synchronize()
+    total = int(offs[-1].item())
+    e0.record()
+    for _ in range(5):
+        expand()
+    e1.record()
+    torch.cuda.synchronize()
+    xms = e0.elapsed_time(e1) / 5
+    mk = total / nb
+    out.update({"boards": nb, "mean_K": mk, "ms_per_expand": xms, "placements_per_sec": total / (xms * 1e-3),
+                "algorithmic_bytes_per_board": board_b(mk), "placements_roofline_frac": board_b(mk) * nb / (xms * 1e-3) / 1e9 / peak})
+    eng.close()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- main
@@ -406,6 +482,10 @@ def main():
                                           "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_board": board_bytes(mean_k),
                                           "traffic": ncu_traffic("expand_bytes_per_launch")}}
         w.close()
+        if a.leg == "all" and world == 1:
+            # ---- BASELINE configs[4]: custom field sizes and piece sets at 2^18 games
+            out["custom_sizes"] = [c5_leg(torch, Engine, dev, local, rank, 16, 8, (0, 6), 1 << 18, 1 << 15, peak, min(a.steps, 10)),
+                                   c5_leg(torch, Engine, dev, local, rank, 40, 20, (0, 1, 2, 3, 4, 5, 6), 1 << 18, 1 << 14, peak, min(a.steps, 10))]
         if rank == 0 and a.leg == "all":
             v, sample = cpu_port_leg()
             out["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port", "sample": sample}

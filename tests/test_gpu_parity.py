@@ -151,36 +151,37 @@ def _digest_dev(t):
     return harness.digest(t.cpu().numpy())
 
 
-def test_full_size_properties_1m_games():
-    """BASELINE config 4 (2^20 games): (a) results do not depend on how the batch is split into calls, (b) a step from a
-    snapshot is reproducible, (c) stepping by placement index == stepping by the enumerated keys, (d) the fused reset of
-    finished games == step followed by reset, (e) the sampled games agree with the oracle."""
+@pytest.mark.parametrize("n,H,W,pieces,steps", [(1 << 20, 22, 10, ALL7, 24), (1 << 18, 16, 8, (0, 6), 16), (1 << 18, 40, 20, ALL7, 12)],
+                         ids=["c4_1m_22x10", "c5_256k_16x8_p06", "c5_256k_40x20"])
+def test_full_size_properties(n, H, W, pieces, steps):
+    """BASELINE configs 4 and 5 at their full sizes (2^20 games 22x10; 2^18 games 16x8 with pieces [0,6] and 40x20): (a) results do
+    not depend on how the batch is split into calls, (b) a step from a snapshot is reproducible, (c) stepping by placement
+    index == stepping by the enumerated keys, (d) the sampled games agree with the oracle."""
     import torch
     from b200tetris import Engine
-    n = 1 << 20
     dev = torch.device("cuda:0")
-    e = Engine(n)
+    e = Engine(n, H, W, pieces)
     gid = torch.arange(n, device=dev, dtype=torch.int64)
     seeds = torch.from_numpy(harness.seeds_for(np.arange(n), np.zeros(n, int)).astype(np.int64)).to(dev).to(torch.int32)
     e.reset_dev(seeds.view(torch.int32))
     K = torch.empty(n, dtype=torch.int32, device=dev)
     reward = torch.empty(n, dtype=torch.int8, device=dev); done = torch.empty(n, dtype=torch.uint8, device=dev)
     lines = torch.empty((n, 2), dtype=torch.uint8, device=dev)
-    field = torch.empty((n, 2, 22, 10), dtype=torch.uint8, device=dev); vec = torch.empty((n, 2, 19), dtype=torch.uint8, device=dev)
-    sample = np.arange(0, n, 4099)[:250].astype(np.int32)
-    lead = pyoracle.OracleVector(len(sample))
+    field = torch.empty((n, 2, H, W), dtype=torch.uint8, device=dev); vec = torch.empty((n, 2, 19), dtype=torch.uint8, device=dev)
+    sample = np.arange(0, n, 4099 if W <= 10 else 16411)[:250].astype(np.int32)
+    lead = pyoracle.OracleVector(len(sample), H, W, pieces)
     lead.reset(harness.seeds_for(sample, np.zeros(len(sample), int)))
-    keys_all = torch.empty((n, 96, 32), dtype=torch.uint8, device=dev) if False else None
-    for t in range(24):
+    okmax, olmax = (256, 128) if W > 10 else (96, 64)
+    for t in range(steps):
         player = ((gid + t) & 1).to(torch.uint8)
         e.enumerate_dev(player, K)
         h = torch.from_numpy(harness.splitmix64(1, np.arange(n), t).astype(np.int64)).to(dev)
         sel = (h.remainder(1 << 30) % K.to(torch.int64)).to(torch.int32)
-        if t == 10:
+        if t == steps // 2:
             e.snapshot(0)
         e.step_dev(player, placement=sel, reward=reward, done=done, lines=lines, field=field, vec=vec)
         torch.cuda.synchronize()
-        if t == 10:
+        if t == steps // 2:
             ref = (_digest_dev(reward), _digest_dev(done), _digest_dev(field), _digest_dev(vec))
             # (b) reproducible from the snapshot, (a) in two half-batches given as explicit index lists
             e.restore(0)
@@ -193,7 +194,7 @@ def test_full_size_properties_1m_games():
             torch.cuda.synchronize()
             assert ref == (_digest_dev(reward), _digest_dev(done), _digest_dev(field), _digest_dev(vec))
         # (e) oracle on the sample, driven by the same placement indices
-        Ko, keys_o, klen_o = lead.enumerate(player[sample].cpu().numpy())[:3]
+        Ko, keys_o, klen_o = lead.enumerate(player[sample].cpu().numpy(), kmax=okmax, lmax=olmax)[:3]
         assert np.array_equal(Ko, K[sample].cpu().numpy())
         so = sel[sample].cpu().numpy()
         ro = lead.step(player[sample].cpu().numpy(), keys_o[np.arange(len(sample)), so], klen_o[np.arange(len(sample)), so])
@@ -212,7 +213,7 @@ def test_full_size_properties_1m_games():
                 lead.reset(harness.seeds_for(sample[ds], np.full(len(ds), t + 1)), ds)
     torch.cuda.synchronize()
     st = e.stats()
-    assert st["garbage_queue_overflow"] == 0 and st["capacity_overflow"] == 0 and st["env_steps"] >= 24 * n - st["episodes"] * 2
+    assert st["garbage_queue_overflow"] == 0 and st["capacity_overflow"] == 0 and st["env_steps"] >= steps * n - st["episodes"] * 2
     e.close()
 
 
