@@ -378,7 +378,7 @@ def main():
     if not a.no_extras and a.leg == "all":
         # ---- end-to-end through the C ABI with HOST buffers (b2t_step_host): H2D of the step's inputs, D2H of reward/done and
         # of the observation tensors, inside the timed region
-        e2e_steps = max(2, min(a.steps, 5))
+        e2e_steps = max(2, min(a.steps, 10))
         import ctypes as C
         from b200tetris.engine import _hp
         def pinned(t):   # numpy view of a pinned host copy of a device tensor
@@ -389,35 +389,52 @@ def main():
         h_field = torch.empty((n, 2, H, W), dtype=torch.uint8).pin_memory().numpy(); h_vec = torch.empty((n, 2, 19), dtype=torch.uint8).pin_memory().numpy()
         h_pidx = torch.empty((n, 2), dtype=torch.uint8).pin_memory().numpy()
 
-        def host_step(t, want_obs):
-            """perform_action through the C ABI with HOST buffers: b2t_step_host copies this step's inputs (player, keys, key_len, reset
-            seeds) from pinned host memory to the device, launches the step and copies reward/done(/observations) back."""
+        def pack4(k):     # two 4-bit key tokens per byte, low nibble first (B2T_KEYS_PACKED4)
+            return np.ascontiguousarray(k[:, 0::2] | (k[:, 1::2] << 4))
+        hp4 = [torch.from_numpy(pack4(hk[t][0])).pin_memory().numpy() for t in range(R)]
+
+        def host_step(t, mode, want_obs=False):
+            """perform_action through the C ABI with HOST buffers: b2t_step_host copies this step's inputs from pinned host memory to
+            the device, launches the step and copies reward/done/lines (and, on request, the observations) back.
+              lean:     keys as one code per byte in zero-terminated rows + acting player; rounds that end restart with engine-chosen
+                        seeds (as the reference's restart from its clock)                                              17 B/game
+              explicit: + key lengths and caller-chosen reset seeds                                                    22 B/game
+              packed:   lean with 4-bit key tokens                                                                      9 B/game"""
             k, ln, sd, pl = hk[t % R]
-            rc = eng.lib.b2t_step_host(eng._h, None, n, _hp(pl, C.c_uint8), _hp(k, C.c_uint8), _hp(ln, C.c_uint8), k.shape[1], None, 1, 0,
-                                       _hp(sd, C.c_uint32), _hp(h_rew, C.c_int8), _hp(h_done, C.c_uint8), _hp(h_lines, C.c_uint8),
+            keys, lens, seeds, fmt, auto = k, None, None, 0, 1
+            if mode == "explicit":
+                lens, seeds, auto = ln, sd, 0
+            elif mode == "packed":
+                keys, fmt = hp4[t % R], 1
+            rc = eng.lib.b2t_step_host(eng._h, None, n, _hp(pl, C.c_uint8), _hp(keys, C.c_uint8), _hp(lens, C.c_uint8), k.shape[1], None, 1, 0,
+                                       _hp(seeds, C.c_uint32), _hp(h_rew, C.c_int8), _hp(h_done, C.c_uint8), _hp(h_lines, C.c_uint8),
                                        _hp(h_field, C.c_uint8) if want_obs else None, _hp(h_vec, C.c_uint8) if want_obs else None,
-                                       _hp(h_pidx, C.c_uint8) if want_obs else None, None)
+                                       _hp(h_pidx, C.c_uint8) if want_obs else None, None, fmt, auto)
             assert rc == 0
 
         times = []
-        for want_obs in (False, True):
-            host_step(0, want_obs)
+        for mode, want_obs in (("lean", False), ("explicit", False), ("packed", False), ("lean", True)):
+            host_step(0, mode, want_obs)
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()
             for t in range(e2e_steps):
-                host_step(t + 1, want_obs)
+                host_step(t + 1, mode, want_obs)
             times.append(time.perf_counter() - t0)
         e2e = torch.tensor(times, device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
-        h2d = n * (hk[0][0].shape[1] + 1 + 1 + 4)
-        out["e2e"] = {"value": n * world * e2e_steps / float(e2e[0]), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
-                      "d2h_bytes_per_step": n * 4, "steps": e2e_steps,
-                      "api": "b2t_step_host: pinned host player/keys/key_len/reset_seeds -> device, fused step, reward/done/lines -> pinned host "
-                             "(the result perform_action returns, tetris_environment_vector.py:79-86); observation tensors stay in HBM for the consumer",
-                      "with_observation_copy": {"value": n * world * e2e_steps / float(e2e[1]), "d2h_bytes_per_step": n * (4 + OBS_BYTES),
+        lm = hk[0][0].shape[1]
+        rate = lambda j: n * world * e2e_steps / float(e2e[j])
+        out["e2e"] = {"value": rate(0), "unit": "env-steps/s", "h2d_bytes_per_step": n * (lm + 1), "d2h_bytes_per_step": n * 4, "steps": e2e_steps,
+                      "api": "b2t_step_host: pinned host keys (one code per byte, zero-terminated rows of %d) + acting player -> device, fused "
+                             "step with engine-chosen seeds for the rounds that restart, reward/done/lines -> pinned host (the result "
+                             "perform_action returns, tetris_environment_vector.py:79-86); observation tensors stay in HBM for the consumer. "
+                             "The call is bound by the host-to-device copy (PCIe), not by the kernel." % lm,
+                      "variants": {"explicit_key_len_and_reset_seeds": {"value": rate(1), "h2d_bytes_per_step": n * (lm + 1 + 1 + 4)},
+                                   "packed_4bit_keys": {"value": rate(2), "h2d_bytes_per_step": n * (lm // 2 + 1)}},
+                      "with_observation_copy": {"value": rate(3), "d2h_bytes_per_step": n * (4 + OBS_BYTES),
                                                 "note": "same call also copying the 480 B/game uint8 state_dict tensors to pinned host memory"}}
 
     if not a.no_extras:

@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("B2T_LIB") or os.path.join(_HERE, "libb200tetris.so") 
 VEC_LEN = 19
 U8, F16, BF16, F32 = 0, 1, 2, 3   # b2t_dtype
 FLAG_TILES = 1                    # b2t_config.flags
+KEYS_U8, KEYS_PACKED4 = 0, 1      # b2t_step_args.key_format
 SNAPSHOT_SLOTS = 4
 
 OK, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4, -5
@@ -22,7 +23,7 @@ u8p, i8p, i32p, u32p, u64p, vp = (C.POINTER(C.c_uint8), C.POINTER(C.c_int8), C.P
 class Config(C.Structure):
     _fields_ = [("n_games", C.c_int32), ("n_players", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
                 ("piece_map", C.c_uint8 * 7), ("bar_null_moves", C.c_uint8), ("time_ms_per_action", C.c_int32),
-                ("piece_stream_len", C.c_int32), ("hole_stream_len", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32)]
+                ("piece_stream_len", C.c_int32), ("hole_stream_len", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32), ("seed", C.c_uint32)]
 
 
 class Info(C.Structure):
@@ -37,7 +38,7 @@ class Obs(C.Structure):
 class StepArgs(C.Structure):
     _fields_ = [("d_game_idx", vp), ("n", C.c_int32), ("d_player", vp), ("d_keys", vp), ("d_key_len", vp), ("lmax", C.c_int32),
                 ("d_placement", vp), ("finalize", C.c_int32), ("time_ms", C.c_int32), ("d_reset_seeds", vp),
-                ("d_reward", vp), ("d_done", vp), ("d_lines", vp), ("obs", Obs)]
+                ("d_reward", vp), ("d_done", vp), ("d_lines", vp), ("obs", Obs), ("key_format", C.c_int32), ("auto_reset", C.c_int32)]
 
 
 class ExpandArgs(C.Structure):
@@ -82,7 +83,7 @@ SYMBOLS = {
     "b2t_stats": (C.c_int, [vp, u64p, vp]),
     "b2t_reset_host": (C.c_int, [vp, i32p, C.c_int32, u32p]),
     "b2t_step_host": (C.c_int, [vp, i32p, C.c_int32, u8p, u8p, u8p, C.c_int32, i32p, C.c_int32, C.c_int32, u32p,
-                                i8p, u8p, u8p, u8p, u8p, u8p, i32p]),
+                                i8p, u8p, u8p, u8p, u8p, u8p, i32p, C.c_int32, C.c_int32]),
     "b2t_observe_host": (C.c_int, [vp, i32p, C.c_int32, u8p, u8p, u8p, i32p]),
     "b2t_enumerate_host": (C.c_int, [vp, i32p, C.c_int32, u8p, i32p, u8p, u8p, C.c_int32, C.c_int32]),
     "b2t_expand_host": (C.c_int, [vp, i32p, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32, i32p, i32p, i32p,

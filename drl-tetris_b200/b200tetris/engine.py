@@ -34,7 +34,7 @@ def _np(a, dtype, n=None):
 
 class Engine:
     def __init__(self, n_games, height=22, width=10, pieces=(0, 1, 2, 3, 4, 5, 6), n_players=2, bar_null_moves=True,
-                 time_ms_per_action=400, piece_stream_len=0, hole_stream_len=0, device=0, tiles=False):
+                 time_ms_per_action=400, piece_stream_len=0, hole_stream_len=0, device=0, tiles=False, seed=0):
         """tiles: keep the raw cell values 1..8 of states[p].field (B2T_FLAG_TILES) — get_game / set_game then carry colours"""
         self._h = None
         self.lib = _lib.load()
@@ -48,6 +48,7 @@ class Engine:
         cfg.time_ms_per_action = int(time_ms_per_action)
         cfg.piece_stream_len, cfg.hole_stream_len = int(piece_stream_len), int(hole_stream_len)
         cfg.device, cfg.flags = self.device, (_lib.FLAG_TILES if tiles else 0)
+        cfg.seed = int(seed) & 0xFFFFFFFF
         h = C.c_void_p()
         rc = self.lib.b2t_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -86,7 +87,7 @@ class Engine:
         self._ck(self.lib.b2t_reset_host(self._h, _hp(idx, C.c_int32), n, _hp(seeds, C.c_uint32)))
 
     def step(self, player, keys=None, key_len=None, idx=None, time_ms=0, finalize=True, placement=None, reset_seeds=None,
-             want_obs=False, want_scalars=False):
+             want_obs=False, want_scalars=False, packed_keys=False, auto_reset=False):
         """perform_action for the listed games.  Returns (reward_base i8[n], done u8[n], lines u8[n,2]) and, with
         want_obs, also (field, vec, piece_idx) after the step; with want_scalars the raw State scalars [n,2,8]."""
         idx, n = self._idx(idx)
@@ -95,7 +96,7 @@ class Engine:
         key_len = _np(key_len, np.uint8, n)
         placement = _np(placement, np.int32, n)
         reset_seeds = _np(reset_seeds, np.uint32, n)
-        lmax = keys.shape[1] if keys is not None else 0
+        lmax = (keys.shape[1] * (2 if packed_keys else 1)) if keys is not None else 0
         reward = np.empty(n, np.int8); done = np.empty(n, np.uint8); lines = np.empty((n, 2), np.uint8)
         field = np.empty((n, 2, self.H, self.W), np.uint8) if want_obs else None
         vec = np.empty((n, 2, VEC_LEN), np.uint8) if want_obs else None
@@ -104,7 +105,8 @@ class Engine:
         self._ck(self.lib.b2t_step_host(self._h, _hp(idx, C.c_int32), n, _hp(player, C.c_uint8), _hp(keys, C.c_uint8),
                                         _hp(key_len, C.c_uint8), lmax, _hp(placement, C.c_int32), int(bool(finalize)), int(time_ms),
                                         _hp(reset_seeds, C.c_uint32), _hp(reward, C.c_int8), _hp(done, C.c_uint8), _hp(lines, C.c_uint8),
-                                        _hp(field, C.c_uint8), _hp(vec, C.c_uint8), _hp(pidx, C.c_uint8), _hp(scal, C.c_int32)))
+                                        _hp(field, C.c_uint8), _hp(vec, C.c_uint8), _hp(pidx, C.c_uint8), _hp(scal, C.c_int32),
+                                        int(bool(packed_keys)), int(bool(auto_reset))))
         out = (reward, done, lines)
         if want_obs:
             out = out + ((field, vec, pidx),)
@@ -244,12 +246,14 @@ class Engine:
         self._ck(self.lib.b2t_select(self._h, self._dp(scores), self._dp(offsets), placement.numel(), self._dp(placement), self._stream()))
 
     def step_dev(self, player, keys=None, key_len=None, idx=None, placement=None, finalize=True, time_ms=0, reset_seeds=None,
-                 reward=None, done=None, lines=None, field=None, vec=None, piece_idx=None, scalars=None, perspective=False):
+                 reward=None, done=None, lines=None, field=None, vec=None, piece_idx=None, scalars=None, perspective=False,
+                 packed_keys=False, auto_reset=False):
         a = _lib.StepArgs()
         a.d_game_idx = self._dp(idx)
         a.n = self.n if idx is None else idx.numel()
         a.d_player, a.d_keys, a.d_key_len = self._dp(player), self._dp(keys), self._dp(key_len)
-        a.lmax = keys.shape[1] if keys is not None else 0
+        a.lmax = (keys.shape[1] * (2 if packed_keys else 1)) if keys is not None else 0
+        a.key_format, a.auto_reset = int(bool(packed_keys)), int(bool(auto_reset))
         a.d_placement = self._dp(placement)
         a.finalize, a.time_ms = int(bool(finalize)), int(time_ms)
         a.d_reset_seeds = self._dp(reset_seeds)

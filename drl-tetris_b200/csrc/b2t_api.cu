@@ -233,13 +233,16 @@ int b2t_step(b2t_handle* h, const b2t_step_args* a, void* stream) { return step_
 static int step_launch(b2t_handle* h, const b2t_step_args* a, int32_t game0, void* stream) {
     if (!h || !a) return B2T_ERR_ARG;
     if (a->n < 0 || game0 < 0 || a->n + game0 > h->cfg.n_games || !a->d_player) return fail(h, B2T_ERR_ARG, "b2t_step: bad n or NULL d_player%s");
-    if (!a->d_placement && (!a->d_keys || !a->d_key_len || a->lmax < 1)) return fail(h, B2T_ERR_ARG, "b2t_step: need d_placement or d_keys+d_key_len+lmax%s");
+    if (!a->d_placement && (!a->d_keys || a->lmax < 1)) return fail(h, B2T_ERR_ARG, "b2t_step: need d_placement or d_keys+lmax%s");
+    if (a->key_format != B2T_KEYS_U8 && a->key_format != B2T_KEYS_PACKED4) return fail(h, B2T_ERR_ARG, "b2t_step: bad key_format%s");
+    if (a->key_format == B2T_KEYS_PACKED4 && (a->lmax & 7)) return fail(h, B2T_ERR_ARG, "b2t_step: packed keys need lmax to be a multiple of 8%s");
     if (a->d_placement && !h->enumerated) return fail(h, B2T_ERR_STATE, "b2t_step: d_placement needs a prior b2t_enumerate/b2t_expand%s");
     if (int r = check_obs(h, a->obs)) return r;
     CK(cudaSetDevice(h->cfg.device));
     KParams p; base_params(h, p);
     p.idx = a->d_game_idx; p.game0 = game0; p.n = a->n; p.player = a->d_player;
     p.keys = a->d_keys; p.key_len = a->d_key_len; p.lmax = a->lmax; p.placement = a->d_placement;
+    p.key_fmt = a->key_format; p.auto_reset = a->auto_reset ? 1 : 0; p.seed_base = h->cfg.seed;
     p.flags = KF_STEP | KF_STORE | (a->finalize ? KF_FINALIZE : 0u);
     if (a->time_ms > 0) p.elapsed = a->time_ms;
     p.reset_seeds = a->d_reset_seeds;
@@ -520,14 +523,15 @@ int b2t_reset_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint32_
 int b2t_step_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint8_t* h_player, const uint8_t* h_keys, const uint8_t* h_key_len,
                   int32_t lmax, const int32_t* h_placement, int32_t finalize, int32_t time_ms, const uint32_t* h_reset_seeds,
                   int8_t* h_reward, uint8_t* h_done, uint8_t* h_lines, uint8_t* h_field, uint8_t* h_vec, uint8_t* h_piece_idx,
-                  int32_t* h_scalars) {
+                  int32_t* h_scalars, int32_t key_format, int32_t auto_reset) {
     if (!h) return B2T_ERR_ARG;
     if (n < 0 || n > h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_step_host: bad n%s");
     CK(cudaSetDevice(h->cfg.device));
     const size_t N = (size_t)n, HW = (size_t)h->ops->H * h->ops->W;
     In idx, pl, keys, klen, plc, rs;
     idx.src = h_idx; idx.bytes = N * 4; pl.src = h_player; pl.bytes = N;
-    keys.src = h_keys; keys.bytes = N * (size_t)(lmax > 0 ? lmax : 0); klen.src = h_key_len; klen.bytes = N;
+    const size_t key_row = (size_t)(lmax > 0 ? lmax : 0) >> (key_format == B2T_KEYS_PACKED4 ? 1 : 0);
+    keys.src = h_keys; keys.bytes = N * key_row; klen.src = h_key_len; klen.bytes = N;
     plc.src = h_placement; plc.bytes = N * 4; rs.src = h_reset_seeds; rs.bytes = N * 4;
     Out rew, done, lines, field, vec, pidx, scal;
     rew.dst = h_reward; rew.bytes = N; done.dst = h_done; done.bytes = N; lines.dst = h_lines; lines.bytes = 2 * N;
@@ -538,7 +542,7 @@ int b2t_step_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint8_t*
         // slice overlap the kernel of another (a step of 2^20 games is 23 MB in, 0.25 ms of kernel, 4 MB out).
         std::vector<In*> ins = {&idx, &pl, &keys, &klen, &plc, &rs};
         std::vector<Out*> outs = {&rew, &done, &lines, &field, &vec, &pidx, &scal};
-        const size_t in_row[6] = {4, 1, (size_t)(lmax > 0 ? lmax : 0), 1, 4, 4};
+        const size_t in_row[6] = {4, 1, key_row, 1, 4, 4};
         const size_t out_row[7] = {1, 1, 2, 2 * HW, 2 * B2T_VEC_LEN, 2, 64};
         size_t total = 0;
         for (auto i : ins) if (i->src) total += (i->bytes + 255) & ~(size_t)255;
@@ -571,7 +575,7 @@ int b2t_step_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint8_t*
             a.d_game_idx = (const int32_t*)din(idx, 0); a.n = cnt; a.d_player = (const uint8_t*)din(pl, 1);
             a.d_keys = (const uint8_t*)din(keys, 2); a.d_key_len = (const uint8_t*)din(klen, 3); a.lmax = lmax;
             a.d_placement = (const int32_t*)din(plc, 4); a.finalize = finalize; a.time_ms = time_ms;
-            a.d_reset_seeds = (const uint32_t*)din(rs, 5);
+            a.d_reset_seeds = (const uint32_t*)din(rs, 5); a.key_format = key_format; a.auto_reset = auto_reset;
             a.d_reward = (int8_t*)dout(rew, 0); a.d_done = (uint8_t*)dout(done, 1); a.d_lines = (uint8_t*)dout(lines, 2);
             a.obs.d_field = dout(field, 3); a.obs.d_vec = dout(vec, 4);
             a.obs.d_piece_idx = (uint8_t*)dout(pidx, 5); a.obs.d_scalars = (int32_t*)dout(scal, 6);
@@ -600,7 +604,7 @@ int b2t_step_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint8_t*
     a.d_game_idx = (const int32_t*)dev_in(h->in, idx); a.n = n; a.d_player = (const uint8_t*)dev_in(h->in, pl);
     a.d_keys = (const uint8_t*)dev_in(h->in, keys); a.d_key_len = (const uint8_t*)dev_in(h->in, klen); a.lmax = lmax;
     a.d_placement = (const int32_t*)dev_in(h->in, plc); a.finalize = finalize; a.time_ms = time_ms;
-    a.d_reset_seeds = (const uint32_t*)dev_in(h->in, rs);
+    a.d_reset_seeds = (const uint32_t*)dev_in(h->in, rs); a.key_format = key_format; a.auto_reset = auto_reset;
     a.d_reward = (int8_t*)dev_out(h->out, rew); a.d_done = (uint8_t*)dev_out(h->out, done); a.d_lines = (uint8_t*)dev_out(h->out, lines);
     a.obs.d_field = (uint8_t*)dev_out(h->out, field); a.obs.d_vec = (uint8_t*)dev_out(h->out, vec);
     a.obs.d_piece_idx = (uint8_t*)dev_out(h->out, pidx); a.obs.d_scalars = (int32_t*)dev_out(h->out, scal);

@@ -428,8 +428,8 @@ struct PS {
     uint32_t piece_ctr;
     // word 12   (hi12: player 0 = seed16, player 1 = game flags)
     uint32_t hole_ctr : 16, hi12 : 16;
-    // word 13
-    uint32_t gq_n : 8, flags : 8, : 16;
+    // word 13   (episode: player 0 only — rounds this game has started, the counter behind engine-chosen reset seeds)
+    uint32_t gq_n : 8, flags : 8, episode : 16;
     // GarbageHandler::garbage (Garbage.h:27): the queue is almost always empty, so it lives in (shared) memory, not in
     // registers: 9 words, word j at gq[j*S]: 0..2 = six int16 counts, 3..8 = six int32 release times (state words 14..22)
     uint32_t* gq;
@@ -462,7 +462,7 @@ B2T_HD void ps_pack(const PS& s, uint32_t* w) {
     u.s = s;
 #pragma unroll
     for (int i = 0; i < 14; i++) w[i] = u.w[i];
-    w[0] &= 0x03FFFFFFu; w[13] &= 0xFFFFu;      // padding bits are stored as zero
+    w[0] &= 0x03FFFFFFu;                        // padding bits are stored as zero
     w[23] = 0;   // words 14..22 (the garbage queue) never pass through registers
 }
 
@@ -797,6 +797,15 @@ B2T_HD void reset_game(PS& p0, const Board<G, S>& b0, PS& p1, const Board<G, S>&
     restart_and_seed<G, S>(p0, b0, tb, seed16);
     restart_and_seed<G, S>(p1, b1, tb, seed16);
     gf = ((winner + 1) << GF_WINNER_SHIFT);
+}
+
+// Engine-chosen seed of a round (b2t_step_args.auto_reset): what time(NULL) is to the reference (PythonHandle.cpp:68-71) — any
+// value will do, only its low 16 bits matter — as a counter hash of (handle seed, game id, rounds started), so a run is
+// reproducible and independent of how games are batched or sharded.
+B2T_HD uint32_t auto_seed(uint32_t base, uint32_t game, uint32_t episode) {
+    uint32_t z = base + game * 0x9E3779B1u + episode * 0x85EBCA77u;
+    z ^= z >> 15; z *= 0x2C1B3C6Du; z ^= z >> 12; z *= 0x297A2D39u; z ^= z >> 15;
+    return z & 0xFFFFu;
 }
 
 // tetris_environment.py:135-149 reward_fcn, extra_rewards=False

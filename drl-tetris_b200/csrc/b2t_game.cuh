@@ -118,6 +118,7 @@ template <class G, int S> B2T_HD void game_reset(Game<G, S>& g, const Tabs& tb, 
     int gf = g.gf();
     const uint32_t s16 = seed & 0xFFFFu;
     reset_game<G, S>(g.p[0], g.b[0], g.p[1], g.b[1], tb, s16, gf);
+    g.p[0].episode = (g.p[0].episode + 1u) & 0xFFFFu;
     g.p[0].hi12 = s16;
     g.p[1].hi12 = (uint32_t)gf & 0xFFFFu;   // round_over and env_done cleared (tetris_environment.py:66-68)
 }

@@ -54,7 +54,10 @@ struct KParams {
     const uint32_t* seeds;        // KF_RESET
     const uint8_t* player;        // KF_STEP / KF_EXPAND
     const uint8_t* keys;
-    const uint8_t* key_len;
+    const uint8_t* key_len;       // NULL: rows are zero-terminated (the length is the position of the last non-zero key)
+    int32_t key_fmt;              // 0: one key code per byte; 1: 4-bit tokens, two per byte (low nibble first), lmax/2 bytes per row
+    int32_t auto_reset;           // fused reset with engine-chosen seeds (auto_seed) when reset_seeds == NULL
+    uint32_t seed_base;
     int32_t lmax;
     const int32_t* placement;
     const uint32_t* plc;          // placement cache [n_games][KMAX][KEYW]
@@ -370,14 +373,14 @@ __global__ void __launch_bounds__(TPB, MODE == GM_EXPAND ? B2T_GAME_MINB + 1 : B
             gi = p.idx ? p.idx[i] : i + p.game0;
             if (stepping) {
                 player = p.player[i] ? 1 : 0;
-                if (p.placement) sel = p.placement[i]; else nkeys = p.key_len[i];
+                if (p.placement) sel = p.placement[i]; else nkeys = p.key_len ? (int)p.key_len[i] : -1;
             }
         }
         obs_player = player;
         const bool by_cache = stepping && (expand || p.placement);
         // fast path: key rows of 16 or 32 bytes, 16-byte aligned, fetched as one or two 128-bit loads
         constexpr int KQ = 2;
-        const bool key_vec = stepping && !by_cache && (p.lmax == 16 || p.lmax == 32) && ((reinterpret_cast<uintptr_t>(p.keys) & 15) == 0);
+        const bool key_vec = stepping && !by_cache && p.key_fmt == 0 && (p.lmax == 16 || p.lmax == 32) && ((reinterpret_cast<uintptr_t>(p.keys) & 15) == 0);
         // (issuing the key loads here, ahead of the state, or prefetching the piece-stream entries was measured slower: the extra
         // live registers cost more than the exposed latency)
         int kc = 0;
@@ -424,9 +427,34 @@ __global__ void __launch_bounds__(TPB, MODE == GM_EXPAND ? B2T_GAME_MINB + 1 : B
                     if (q.w) nkeys = (4 * j + 3) * 8 + (msb32(q.w) >> 2) + 1;
                 }
             } else {
-                if (nkeys > KW * 8) nkeys = KW * 8;
+                const bool zterm = nkeys < 0;            // zero-terminated row: every token counts, the length follows from the words
+                if (zterm || nkeys > KW * 8) nkeys = KW * 8;
                 if (nkeys > p.lmax) nkeys = p.lmax;
-                if (key_vec) {
+                if (p.key_fmt == 1) {                    // packed tokens: the row already is the working form
+                    const uint8_t* kp = p.keys + (size_t)i * (size_t)(p.lmax >> 1);
+                    uint32_t w[KW];
+                    const bool al = (reinterpret_cast<uintptr_t>(p.keys) & 15) == 0;
+                    if (p.lmax == 16 && al) {
+                        const uint2 q = *reinterpret_cast<const uint2*>(kp);
+#pragma unroll
+                        for (int j = 0; j < KW; j++) w[j] = j == 0 ? q.x : j == 1 ? q.y : 0u;
+                    } else if (p.lmax == 32 && al && KW >= 4) {
+                        const uint4 q = *reinterpret_cast<const uint4*>(kp);
+#pragma unroll
+                        for (int j = 0; j < KW; j++) w[j] = j == 0 ? q.x : j == 1 ? q.y : j == 2 ? q.z : j == 3 ? q.w : 0u;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < KW; j++) {
+                            uint32_t v = 0;
+#pragma unroll
+                            for (int b = 0; b < 4; b++)
+                                if (8 * j + 2 * b < p.lmax) v |= (uint32_t)kp[4 * j + b] << (8 * b);
+                            w[j] = v;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < KW; j++) kw[j * WS] = w[j];
+                } else if (key_vec) {
                     uint4 kq[KQ];
                     {
                         const uint8_t* kp = p.keys + (size_t)i * (size_t)p.lmax;
@@ -447,6 +475,15 @@ __global__ void __launch_bounds__(TPB, MODE == GM_EXPAND ? B2T_GAME_MINB + 1 : B
                     pack_keys<KW>(kp, nkeys, tmp);
 #pragma unroll
                     for (int j = 0; j < KW; j++) kw[j * WS] = tmp[j];
+                }
+                if (zterm) {
+                    nkeys = 1;
+#pragma unroll
+                    for (int j = 0; j < KW; j++) {
+                        const uint32_t w = kw[j * WS];
+                        if (w) nkeys = j * 8 + (msb32(w) >> 2) + 1;
+                    }
+                    if (nkeys > p.lmax) nkeys = p.lmax;
                 }
             }
             const bool was_over = (g.gf() & GF_ROUND_OVER) != 0;
@@ -489,7 +526,8 @@ __global__ void __launch_bounds__(TPB, MODE == GM_EXPAND ? B2T_GAME_MINB + 1 : B
                     st_both = d0 && d1; st_w0 = !d0 && d1; st_w1 = d0 && !d1;
                 }
             }
-            if (!expand && done && p.reset_seeds) game_reset(g, tb, p.reset_seeds[i]);
+            if (!expand && done && (p.reset_seeds || p.auto_reset))
+                game_reset(g, tb, p.reset_seeds ? p.reset_seeds[i] : auto_seed(p.seed_base, (uint32_t)gi, g.p[0].episode));
         }
         const int flags_after = g.p[0].flags | g.p[1].flags;
         st_gq = ((flags_after & ~flags_before) & 1) != 0;

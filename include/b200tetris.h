@@ -50,6 +50,7 @@ typedef struct {
     int32_t hole_stream_len;     /* garbage holes tabulated per seed (0 = default 512) */
     int32_t device;              /* CUDA device ordinal */
     uint32_t flags;              /* B2T_FLAG_* */
+    uint32_t seed;               /* base of the engine-chosen round seeds (b2t_step_args.auto_reset) */
 } b2t_config;
 
 /* Keep the raw cell values of PythonHandle.states[p].field (1..7 = piece.tile, 8 = garbage; gameField.cpp:105-110,
@@ -110,7 +111,8 @@ typedef struct {
     const uint8_t *d_player;       /* [n] acting player 0/1 */
     /* action, one of: */
     const uint8_t *d_keys;         /* [n, lmax] key codes 0..10 (others ignored, PythonHandle.cpp:109-110) */
-    const uint8_t *d_key_len;      /* [n] */
+    const uint8_t *d_key_len;      /* [n], or NULL: rows are zero-terminated (key 0 is a no-op, PythonHandle.cpp:109-110, so the
+                                      length is the position of the last non-zero key) */
     int32_t lmax;
     const int32_t *d_placement;    /* [n] index into the list of the last b2t_enumerate/b2t_expand of that game */
     int32_t finalize;              /* simulate/finalize switch of perform_action; 1 = normal step */
@@ -122,7 +124,14 @@ typedef struct {
     uint8_t *d_done;               /* [n] */
     uint8_t *d_lines;              /* [n,2] states[p].reward = lines cleared since the previous finish (PythonHandle.cpp:176) */
     b2t_obs obs;                   /* state after the call (after the fused reset, if any) */
+    int32_t key_format;            /* B2T_KEYS_U8 (one key code per byte) or B2T_KEYS_PACKED4 (4-bit tokens, two per byte, low nibble
+                                      first; a row is lmax/2 bytes, lmax a multiple of 8; codes 11..15 are no-ops like any other) */
+    int32_t auto_reset;            /* d_reset_seeds == NULL and auto_reset != 0: games that end are reset with an engine-chosen
+                                      seed — a counter hash of (cfg.seed, game id, rounds started), the role time(NULL) plays in
+                                      PythonHandle::seed — so no seeds travel to the device */
 } b2t_step_args;
+#define B2T_KEYS_U8 0
+#define B2T_KEYS_PACKED4 1
 int b2t_step(b2t_handle *h, const b2t_step_args *a, void *stream);
 
 /* get_state + state_dict (tetris_environment.py:131-133; vector :99-101) */
@@ -231,7 +240,7 @@ int b2t_reset_host(b2t_handle *h, const int32_t *h_game_idx, int32_t n, const ui
 int b2t_step_host(b2t_handle *h, const int32_t *h_game_idx, int32_t n, const uint8_t *h_player, const uint8_t *h_keys,
                   const uint8_t *h_key_len, int32_t lmax, const int32_t *h_placement, int32_t finalize, int32_t time_ms,
                   const uint32_t *h_reset_seeds, int8_t *h_reward, uint8_t *h_done, uint8_t *h_lines,
-                  uint8_t *h_field, uint8_t *h_vec, uint8_t *h_piece_idx, int32_t *h_scalars);
+                  uint8_t *h_field, uint8_t *h_vec, uint8_t *h_piece_idx, int32_t *h_scalars, int32_t key_format, int32_t auto_reset);
 int b2t_observe_host(b2t_handle *h, const int32_t *h_game_idx, int32_t n, uint8_t *h_field, uint8_t *h_vec,
                      uint8_t *h_piece_idx, int32_t *h_scalars);
 int b2t_enumerate_host(b2t_handle *h, const int32_t *h_game_idx, int32_t n, const uint8_t *h_player, int32_t *h_K,

@@ -27,12 +27,17 @@ for t in range(4):
     k,ln=bench.sventon_keys(gids,t)
     hk.append((pinned(k),pinned(ln),pinned((bench.splitmix64(0xB200,gids,t+1)&np.uint64(0xFFFF)).astype(np.uint32)),pinned(((gids+t)&1).astype(np.uint8))))
 h_rew=pinned(np.empty(n,np.int8)); h_done=pinned(np.empty(n,np.uint8)); h_lines=pinned(np.empty((n,2),np.uint8))
+MODE=os.environ.get("E2E_MODE","lean")
+hp4=[pinned(np.ascontiguousarray(k[:,0::2]|(k[:,1::2]<<4))) for k,_,_,_ in hk]
 def host_step(t):
     k,ln,sd,pl=hk[t%4]
-    rc=eng.lib.b2t_step_host(eng._h,None,n,_hp(pl,C.c_uint8),_hp(k,C.c_uint8),_hp(ln,C.c_uint8),k.shape[1],None,1,0,_hp(sd,C.c_uint32),_hp(h_rew,C.c_int8),_hp(h_done,C.c_uint8),_hp(h_lines,C.c_uint8),None,None,None,None)
+    keys,lens,seeds,fmt,auto=k,None,None,0,1
+    if MODE=="explicit": lens,seeds,auto=ln,sd,0
+    if MODE=="packed": keys,fmt=hp4[t%4],1
+    rc=eng.lib.b2t_step_host(eng._h,None,n,_hp(pl,C.c_uint8),_hp(keys,C.c_uint8),_hp(lens,C.c_uint8),k.shape[1],None,1,0,_hp(seeds,C.c_uint32),_hp(h_rew,C.c_int8),_hp(h_done,C.c_uint8),_hp(h_lines,C.c_uint8),None,None,None,None,fmt,auto)
     assert rc==0
 for t in range(3): host_step(t)
 t0=time.perf_counter()
 for t in range(10): host_step(t)
 dt=(time.perf_counter()-t0)/10
-print("slices=%s  step_host %.3f ms  %.3e env-steps/s"%(os.environ.get("B2T_PIPE_SLICES","default"),dt*1e3,n/dt))
+print("mode=%s slices=%s  step_host %.3f ms  %.3e env-steps/s"%(MODE,os.environ.get("B2T_PIPE_SLICES","default"),dt*1e3,n/dt))

@@ -598,3 +598,50 @@ def test_tile_colour_planes():
     for i in range(0, n, 5):
         assert np.array_equal(e.get_game(i)[1], snap["f"][i]), i
     e.close()
+
+
+def test_key_formats_and_engine_chosen_seeds():
+    """b2t_step_args.key_format / d_key_len == NULL / auto_reset: zero-terminated rows and 4-bit packed tokens step exactly like
+    explicit-length byte keys (host and device entry points, aligned and odd row widths), and the fused reset with engine-chosen
+    seeds equals a reset with auto_seed(cfg.seed, game, rounds started) computed here."""
+    import torch
+    from b200tetris import Engine
+    n = 3000
+    gids = np.arange(n)
+    s0 = harness.seeds_for(gids, np.zeros(n, int))
+
+    def auto_seed(base, game, episode):
+        z = (base + game * 0x9E3779B1 + episode * 0x85EBCA77) & 0xFFFFFFFF
+        z ^= z >> 15; z = (z * 0x2C1B3C6D) & 0xFFFFFFFF; z ^= z >> 12; z = (z * 0x297A2D39) & 0xFFFFFFFF; z ^= z >> 15
+        return z & 0xFFFF
+    for lmax in (16, 32, 24):
+        a, b, c = Engine(n, seed=12345), Engine(n, seed=12345), Engine(n, seed=12345)
+        for e in (a, b, c):
+            e.reset(s0)
+        episode = np.ones(n, np.int64)                 # every game has started one round
+        pol = harness.Policy("junk", lmax=lmax, salt=5)
+        dev = torch.device("cuda:0")
+        for t in range(60):
+            player = ((gids + t) & 1).astype(np.uint8)
+            keys, klen, _ = pol.choose(None, t, gids, player)
+            # the reference ignores key 0 and trailing keys equally: zero the tail so the row is its own length
+            keys[np.arange(lmax)[None, :] >= klen[:, None]] = 0
+            seeds = np.array([auto_seed(12345, int(g), int(ep)) for g, ep in zip(gids, episode)], np.uint32)
+            ra = a.step(player, keys, klen, reset_seeds=seeds, want_obs=True)
+            rb = b.step(player, keys, None, auto_reset=True, want_obs=True)
+            packed = np.ascontiguousarray(keys[:, 0::2] | (keys[:, 1::2] << 4))
+            f = torch.empty((n, 2, 22, 10), dtype=torch.uint8, device=dev); v = torch.empty((n, 2, 19), dtype=torch.uint8, device=dev)
+            rw = torch.empty(n, dtype=torch.int8, device=dev); dn = torch.empty(n, dtype=torch.uint8, device=dev)
+            c.step_dev(torch.from_numpy(player).to(dev), torch.from_numpy(packed).to(dev), None, packed_keys=True, auto_reset=True,
+                       reward=rw, done=dn, field=f, vec=v)
+            torch.cuda.synchronize()
+            for x, y in zip(ra[:3], rb[:3]):
+                assert np.array_equal(x, y), (lmax, t)
+            for x, y in zip(ra[3], rb[3]):
+                assert np.array_equal(x, y), (lmax, t)
+            assert np.array_equal(ra[0], rw.cpu().numpy()) and np.array_equal(ra[1], dn.cpu().numpy())
+            assert np.array_equal(ra[3][0], f.cpu().numpy()) and np.array_equal(ra[3][1], v.cpu().numpy())
+            episode += ra[1].astype(np.int64)
+        assert episode.max() > 1
+        for e in (a, b, c):
+            e.close()
