@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(TPB, MODE == GM_EXPAND ? B2T_GAME_MINB + 1 : B
         const bool by_cache = stepping && (expand || p.placement);
         // fast path: key rows of 16 or 32 bytes, 16-byte aligned, fetched as one or two 128-bit loads
         constexpr int KQ = 2;
-        const bool key_vec = stepping && !by_cache && p.key_fmt == 0 && (p.lmax == 16 || p.lmax == 32) && ((reinterpret_cast<uintptr_t>(p.keys) & 15) == 0);
+        const bool key_vec = stepping && !by_cache && (MODE != GM_GENERIC || p.key_fmt == 0) && (p.lmax == 16 || p.lmax == 32) && ((reinterpret_cast<uintptr_t>(p.keys) & 15) == 0);
         // (issuing the key loads here, ahead of the state, or prefetching the piece-stream entries was measured slower: the extra
         // live registers cost more than the exposed latency)
         int kc = 0;
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(TPB, MODE == GM_EXPAND ? B2T_GAME_MINB + 1 : B
                 const bool zterm = nkeys < 0;            // zero-terminated row: every token counts, the length follows from the words
                 if (zterm || nkeys > KW * 8) nkeys = KW * 8;
                 if (nkeys > p.lmax) nkeys = p.lmax;
-                if (p.key_fmt == 1) {                    // packed tokens: the row already is the working form
+                if (MODE == GM_GENERIC && p.key_fmt == 1) {   // packed tokens: the row already is the working form (generic variant only)
                     const uint8_t* kp = p.keys + (size_t)i * (size_t)(p.lmax >> 1);
                     uint32_t w[KW];
                     const bool al = (reinterpret_cast<uintptr_t>(p.keys) & 15) == 0;
@@ -1105,7 +1105,7 @@ template <class G> struct Launch {
     static cudaError_t game(const KParams& p, int rows, cudaStream_t s) {
         if (rows <= 0) return cudaSuccess;
         const dim3 grid((rows + TPB - 1) / TPB);
-        if (p.obs_dtype != 0 || (p.tiles && !(p.flags & KF_EXPAND))) game_kernel<G, GM_GENERIC><<<grid, TPB, L::GAME_TOTAL, s>>>(p);
+        if (p.obs_dtype != 0 || p.key_fmt != 0 || (p.tiles && !(p.flags & KF_EXPAND))) game_kernel<G, GM_GENERIC><<<grid, TPB, L::GAME_TOTAL, s>>>(p);
         else if ((p.flags & ~KF_FINALIZE) == KF_EXPAND) game_kernel<G, GM_EXPAND><<<grid, TPB, L::GAME_TOTAL, s>>>(p);
         else if ((p.flags & ~KF_FINALIZE) == (KF_STEP | KF_STORE)) game_kernel<G, GM_STEP><<<grid, TPB, L::GAME_TOTAL, s>>>(p);
         else game_kernel<G, GM_GENERIC><<<grid, TPB, L::GAME_TOTAL, s>>>(p);
