@@ -16,6 +16,8 @@ import numpy as np
 
 from .engine import Engine
 
+_engine_factory = Engine   # tests substitute a CPU double with the same interface; the product has no CPU path
+
 DEFAULTS = {  # experiments/presets.py:123-182 ("default"), the keys that reach the backend
     "game_size": [22, 10], "pieces": [0, 1, 2, 3, 4, 5, 6], "n_players": 2, "bar_null_moves": True,
     "time_elapsed_each_action": 400, "extra_rewards": False, "reward_ammount": (1.0, 0.0), "action_type": "place_block",
@@ -76,7 +78,7 @@ class state:
     def _dict(self, p):
         v = self._vec[p]
         return {"field": self._field[p], "piece": v[12:19], "x": v[0:1], "y": v[1:2], "incoming_lines": v[2:3],
-                "combo_time": np.array(v[3], dtype=np.uint8), "combo_count": v[4:5], "nextpiece": v[5:12],
+                "combo_time": v[3:4], "combo_count": v[4:5], "nextpiece": v[5:12],
                 "piece_idx": int(self._piece_idx[p])}
 
     def __getitem__(self, idx):
@@ -109,7 +111,7 @@ class tetris_environment_vector:
         self.player_idxs = list(range(s["n_players"]))
         self.envs = list(range(n_envs))
         H, W = s["game_size"]
-        self.engine = Engine(n_envs, H, W, s["pieces"], 2, s["bar_null_moves"], s["time_elapsed_each_action"], device=device)
+        self.engine = _engine_factory(n_envs, H, W, s["pieces"], 2, s["bar_null_moves"], s["time_elapsed_each_action"], device=device)
         self._seed0 = int(s.get("seed", time.time()))
         self._episode = np.zeros(n_envs, np.int64)
         self.done = np.zeros(n_envs, bool)
