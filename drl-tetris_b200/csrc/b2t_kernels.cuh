@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(TPB, MODE == GM_EXPAND ? B2T_GAME_MINB + 1 : B
             gi = p.idx ? p.idx[i] : i + p.game0;
             if (stepping) {
                 player = p.player[i] ? 1 : 0;
-                if (p.placement) sel = p.placement[i]; else nkeys = p.key_len ? (int)p.key_len[i] : -1;
+                if (p.placement) sel = p.placement[i]; else nkeys = (MODE != GM_GENERIC || p.key_len) ? (int)p.key_len[i] : -1;
             }
         }
         obs_player = player;
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(TPB, MODE == GM_EXPAND ? B2T_GAME_MINB + 1 : B
                     if (q.w) nkeys = (4 * j + 3) * 8 + (msb32(q.w) >> 2) + 1;
                 }
             } else {
-                const bool zterm = nkeys < 0;            // zero-terminated row: every token counts, the length follows from the words
+                const bool zterm = MODE == GM_GENERIC && nkeys < 0;            // zero-terminated row: every token counts, the length follows from the words
                 if (zterm || nkeys > KW * 8) nkeys = KW * 8;
                 if (nkeys > p.lmax) nkeys = p.lmax;
                 if (MODE == GM_GENERIC && p.key_fmt == 1) {   // packed tokens: the row already is the working form (generic variant only)
@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(TPB, MODE == GM_EXPAND ? B2T_GAME_MINB + 1 : B
                     st_both = d0 && d1; st_w0 = !d0 && d1; st_w1 = d0 && !d1;
                 }
             }
-            if (!expand && done && (p.reset_seeds || p.auto_reset))
+            if (!expand && done && (p.reset_seeds || (MODE == GM_GENERIC && p.auto_reset)))
                 game_reset(g, tb, p.reset_seeds ? p.reset_seeds[i] : auto_seed(p.seed_base, (uint32_t)gi, g.p[0].episode));
         }
         const int flags_after = g.p[0].flags | g.p[1].flags;
@@ -1105,7 +1105,8 @@ template <class G> struct Launch {
     static cudaError_t game(const KParams& p, int rows, cudaStream_t s) {
         if (rows <= 0) return cudaSuccess;
         const dim3 grid((rows + TPB - 1) / TPB);
-        if (p.obs_dtype != 0 || p.key_fmt != 0 || (p.tiles && !(p.flags & KF_EXPAND))) game_kernel<G, GM_GENERIC><<<grid, TPB, L::GAME_TOTAL, s>>>(p);
+        if (p.obs_dtype != 0 || p.key_fmt != 0 || p.auto_reset || ((p.flags & KF_STEP) && !p.placement && !p.key_len) ||
+            (p.tiles && !(p.flags & KF_EXPAND))) game_kernel<G, GM_GENERIC><<<grid, TPB, L::GAME_TOTAL, s>>>(p);
         else if ((p.flags & ~KF_FINALIZE) == KF_EXPAND) game_kernel<G, GM_EXPAND><<<grid, TPB, L::GAME_TOTAL, s>>>(p);
         else if ((p.flags & ~KF_FINALIZE) == (KF_STEP | KF_STORE)) game_kernel<G, GM_STEP><<<grid, TPB, L::GAME_TOTAL, s>>>(p);
         else game_kernel<G, GM_GENERIC><<<grid, TPB, L::GAME_TOTAL, s>>>(p);
