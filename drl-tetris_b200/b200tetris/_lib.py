@@ -88,6 +88,8 @@ SYMBOLS = {
     "b2t_enumerate_host": (C.c_int, [vp, i32p, C.c_int32, u8p, i32p, u8p, u8p, C.c_int32, C.c_int32]),
     "b2t_expand_host": (C.c_int, [vp, i32p, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32, i32p, i32p, i32p,
                                   u8p, u8p, C.c_int32, i8p, u8p, u8p, u8p, u8p, u8p]),
+    "b2t_host_alloc": (C.c_int, [C.c_size_t, C.c_int32, C.POINTER(vp)]),
+    "b2t_host_free": (C.c_int, [vp]),
     "b2t_debug_streams": (C.c_int, [vp, C.c_uint32, C.c_int32, u8p, u8p]),
 }
 

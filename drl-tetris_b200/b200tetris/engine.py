@@ -32,6 +32,23 @@ def _np(a, dtype, n=None):
     return a
 
 
+def host_array(shape, dtype, write_combined=False):
+    """numpy array over pinned host memory from b2t_host_alloc (freed when the array is collected).  write_combined: for inputs the
+    host only writes — the device reads them faster, the host reads them very slowly."""
+    lib = _lib.load()
+    shape = tuple(int(x) for x in (shape if hasattr(shape, "__len__") else (shape,)))
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    rc = lib.b2t_host_alloc(max(nbytes, 1), int(bool(write_combined)), C.byref(p))
+    if rc != 0:
+        raise B2TError(rc, "b2t_host_alloc failed")
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    import weakref
+    weakref.finalize(buf, lib.b2t_host_free, p)
+    return arr
+
+
 class Engine:
     def __init__(self, n_games, height=22, width=10, pieces=(0, 1, 2, 3, 4, 5, 6), n_players=2, bar_null_moves=True,
                  time_ms_per_action=400, piece_stream_len=0, hole_stream_len=0, device=0, tiles=False, seed=0):

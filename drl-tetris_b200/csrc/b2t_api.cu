@@ -448,6 +448,13 @@ int b2t_stats(b2t_handle* h, uint64_t* h_out, void* stream) {
     return B2T_OK;
 }
 
+int b2t_host_alloc(size_t bytes, int32_t write_combined, void** out) {
+    if (!out || !bytes) return B2T_ERR_ARG;
+    *out = nullptr;
+    return cudaHostAlloc(out, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault) == cudaSuccess ? B2T_OK : B2T_ERR_CUDA;
+}
+int b2t_host_free(void* p) { return (!p || cudaFreeHost(p) == cudaSuccess) ? B2T_OK : B2T_ERR_CUDA; }
+
 int b2t_debug_streams(b2t_handle* h, uint32_t seed16, int32_t n, uint8_t* h_pieces, uint8_t* h_holes) {
     if (!h || seed16 >= (uint32_t)RNG_SEEDS || n < 0) return B2T_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));

@@ -19,6 +19,7 @@
 #ifndef B200TETRIS_H
 #define B200TETRIS_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -250,6 +251,12 @@ int b2t_expand_host(b2t_handle *h, const int32_t *h_game_idx, int32_t n, const u
                     int32_t time_ms, int32_t capacity, int32_t *h_K, int32_t *h_offsets, int32_t *h_total,
                     uint8_t *h_keys, uint8_t *h_key_len, int32_t lmax, int8_t *h_reward, uint8_t *h_done, uint8_t *h_lines,
                     uint8_t *h_field, uint8_t *h_vec, uint8_t *h_piece_idx);
+
+/* Pinned host memory for the *_host entry points (buffers allocated here, or pinned by the caller in any other way, are copied
+ * without the staging pass).  write_combined != 0 asks for write-combined pages: slow for the host to READ, but the device's
+ * reads of them skip the CPU cache snoop — use it for inputs the host only writes (keys, players). */
+int b2t_host_alloc(size_t bytes, int32_t write_combined, void **out);
+int b2t_host_free(void *p);
 
 /* Stream-table probe for tests: first n entries of the piece / hole stream of a 16-bit seed. */
 int b2t_debug_streams(b2t_handle *h, uint32_t seed16, int32_t n, uint8_t *h_pieces, uint8_t *h_holes);

@@ -18,15 +18,30 @@ torch.cuda.synchronize(); t0=time.perf_counter()
 for _ in range(20): h4.copy_(d4,non_blocking=True)
 torch.cuda.synchronize(); dt=(time.perf_counter()-t0)/20
 print("D2H 4MiB pinned: %.3f ms  %.1f GB/s"%(dt*1e3, h4.numel()/dt/1e9))
+from b200tetris import host_array
+for wc in (False, True):
+    hb=host_array(23*1024*1024,np.uint8,write_combined=wc); hb[:]=1
+    hbt=torch.from_numpy(hb)
+    for _ in range(3): d.copy_(hbt,non_blocking=True)
+    torch.cuda.synchronize(); t0=time.perf_counter()
+    for _ in range(20): d.copy_(hbt,non_blocking=True)
+    torch.cuda.synchronize(); dt=(time.perf_counter()-t0)/20
+    print("H2D 23MiB b2t_host_alloc wc=%s: %.3f ms  %.1f GB/s"%(wc,dt*1e3,hb.size/dt/1e9))
+WC=os.environ.get("E2E_WC","0")=="1"
 eng=Engine(n)
 gids=np.arange(n)
 eng.reset((bench.splitmix64(0xB200,gids,0)&np.uint64(0xFFFF)).astype(np.uint32))
-def pinned(a): return torch.from_numpy(a).pin_memory().numpy()
+def pinned(a):
+    if WC:
+        h=host_array(a.shape,a.dtype,write_combined=True); h[...]=a; return h
+    return torch.from_numpy(a).pin_memory().numpy()
 hk=[]
 for t in range(4):
     k,ln=bench.sventon_keys(gids,t)
     hk.append((pinned(k),pinned(ln),pinned((bench.splitmix64(0xB200,gids,t+1)&np.uint64(0xFFFF)).astype(np.uint32)),pinned(((gids+t)&1).astype(np.uint8))))
+_wc=WC; WC=False
 h_rew=pinned(np.empty(n,np.int8)); h_done=pinned(np.empty(n,np.uint8)); h_lines=pinned(np.empty((n,2),np.uint8))
+WC=_wc
 MODE=os.environ.get("E2E_MODE","lean")
 hp4=[pinned(np.ascontiguousarray(k[:,0::2]|(k[:,1::2]<<4))) for k,_,_,_ in hk]
 def host_step(t):
@@ -40,4 +55,4 @@ for t in range(3): host_step(t)
 t0=time.perf_counter()
 for t in range(10): host_step(t)
 dt=(time.perf_counter()-t0)/10
-print("mode=%s slices=%s  step_host %.3f ms  %.3e env-steps/s"%(MODE,os.environ.get("B2T_PIPE_SLICES","default"),dt*1e3,n/dt))
+print("wc=%s mode=%s slices=%s  step_host %.3f ms  %.3e env-steps/s"%(WC,MODE,os.environ.get("B2T_PIPE_SLICES","default"),dt*1e3,n/dt))

@@ -11,7 +11,7 @@ import harness
 @pytest.mark.gpu
 def test_c_abi_tour():
     import torch
-    from b200tetris import Engine
+    from b200tetris import Engine, host_array
     dev = torch.device("cuda:0")
     for H, W, pieces, n in ((22, 10, (0, 1, 2, 3, 4, 5, 6), 333), (16, 8, (0, 6), 70), (40, 20, (0, 1, 2, 3, 4, 5, 6), 45)):
         e = Engine(n, H, W, pieces, piece_stream_len=256, hole_stream_len=64, tiles=(W == 10))
@@ -25,6 +25,13 @@ def test_c_abi_tour():
             keys, klen, _ = pol.choose(None, t, gids, player)
             e.step(player, keys, klen, want_obs=True, want_scalars=True)
             e.step(player, keys, None, auto_reset=True)
+            wk = host_array(keys.shape, np.uint8, write_combined=True)      # b2t_host_alloc: pinned, write-combined inputs
+            wk[...] = keys
+            wr = host_array(n, np.int8)
+            import ctypes as C
+            from b200tetris.engine import _hp
+            assert e.lib.b2t_step_host(e._h, None, n, _hp(player, C.c_uint8), _hp(wk, C.c_uint8), None, keys.shape[1], None, 1, 0, None,
+                                       _hp(wr, C.c_int8), None, None, None, None, None, None, 0, 1) == 0
             pl = torch.from_numpy(player).to(dev)
             for dt in (torch.uint8, torch.float16, torch.float32):
                 f = torch.empty((n, 2, H, W), dtype=dt, device=dev); v = torch.empty((n, 2, 19), dtype=dt, device=dev)
