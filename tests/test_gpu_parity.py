@@ -21,6 +21,9 @@ ROLLOUTS = [
     ("sventon", 22, 10, ALL7, 64, 150, 0),
     ("press_key", 22, 10, ALL7, 64, 700, 0),     # action_type "press_key": one key per step, gravity / lockdown place the pieces
     ("press_key", 16, 8, (0, 6), 32, 500, 30),
+    ("greedy", 25, 12, ALL7, 24, 300, 0),          # tallest field on 32-bit columns, W > 10
+    ("random", 25, 12, ALL7, 64, 200, 0),
+    ("junk", 25, 12, ALL7, 32, 200, 9),
     ("random", 16, 8, (0, 6), 96, 200, 0),
     ("greedy", 16, 8, (0, 6), 32, 300, 0),
     ("random", 40, 20, ALL7, 40, 200, 0),

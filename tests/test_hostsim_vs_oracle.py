@@ -23,6 +23,8 @@ CASES = [
     ("sventon", 22, 10, (0, 1, 2, 3, 4, 5, 6), 16, 200, 0),
     ("press_key", 22, 10, (0, 1, 2, 3, 4, 5, 6), 16, 700, 0),
     ("press_key", 16, 8, (0, 6), 8, 500, 30),
+    ("greedy", 25, 12, (0, 1, 2, 3, 4, 5, 6), 6, 260, 0),      # tallest field on 32-bit columns, W > 10
+    ("junk", 25, 12, (0, 1, 2, 3, 4, 5, 6), 8, 200, 9),
     ("random", 16, 8, (0, 6), 16, 300, 0),
     ("greedy", 16, 8, (0, 6), 8, 500, 0),
     ("random", 40, 20, (0, 1, 2, 3, 4, 5, 6), 4, 300, 0),

@@ -25,6 +25,8 @@ CASES = [
     ("greedy", 16, 8, (0, 6), 6, 300, 0),
     ("random", 40, 20, (0, 1, 2, 3, 4, 5, 6), 3, 200, 0),
     ("greedy", 40, 20, (0, 1, 2, 3, 4, 5, 6), 2, 160, 0),
+    ("greedy", 25, 12, (0, 1, 2, 3, 4, 5, 6), 4, 260, 0),    # W > 10 on a field the engine keeps in 32-bit columns
+    ("junk", 25, 12, (0, 1, 2, 3, 4, 5, 6), 4, 160, 9),
     ("random", 10, 6, (2, 3), 8, 120, 0),                    # only_zs, empty placement lists
     ("greedy", 10, 6, (2, 3, 4, 5), 6, 200, 0),
     ("junk", 12, 5, (4,), 4, 120, 5),
