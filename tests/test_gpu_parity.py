@@ -53,6 +53,24 @@ def test_rollout_matches_oracle(kind, H, W, pieces, n, steps, solo):
         assert stats["lines"] > 0 and stats["garbage"] > 0
 
 
+TIMINGS = [  # kind, time_elapsed_each_action, games, steps: gravity tiers (every > 3000 ms: -10 / -5 / -2 / -1, DropDelay.cpp:3-21),
+    ("greedy", 3100, 32, 420),     # lockdown and garbage / combo timers at other cadences than the default 400 ms
+    ("press_key", 3100, 48, 300),
+    ("press_key", 1000, 48, 300),
+    ("greedy", 50, 32, 200),
+    ("junk", 7, 48, 200),
+]
+
+
+@pytest.mark.parametrize("kind,time_ms,n,steps", TIMINGS)
+def test_other_time_steps(kind, time_ms, n, steps):
+    """settings["time_elapsed_each_action"] other than 400 ms, per call (b2t_step_args.time_ms)"""
+    lead = pyoracle.OracleVector(n)
+    dev = _engine(n)
+    stats = harness.rollout_pair(lead, dev, steps, harness.Policy(kind, kmax=96, lmax=32), time_ms=time_ms)
+    assert stats["steps"] == n * steps
+
+
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
 
 

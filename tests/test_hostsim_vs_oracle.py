@@ -46,6 +46,23 @@ def test_core_matches_oracle(kind, H, W, pieces, n, steps, solo):
     assert all(sim.flags(i) == 0 for i in range(n)), "garbage-queue / stream-table overflow flag raised"
 
 
+TIMINGS = [  # kind, time_elapsed_each_action, games, steps: gravity tiers (every > 3000 ms: -10 / -5 / -2 / -1, DropDelay.cpp:3-21),
+    ("greedy", 3100, 4, 420),     # lockdown and garbage / combo timers at other cadences than the default 400 ms
+    ("press_key", 3100, 6, 300),
+    ("press_key", 1000, 6, 300),
+    ("greedy", 50, 4, 200),
+    ("junk", 7, 6, 200),
+]
+
+
+@pytest.mark.parametrize("kind,time_ms,n,steps", TIMINGS)
+def test_other_time_steps(kind, time_ms, n, steps):
+    lead = pyoracle.OracleVector(n)
+    sim = pyhostsim.HostSimVector(n)
+    stats = harness.rollout_pair(lead, sim, steps, harness.Policy(kind, kmax=96, lmax=32), time_ms=time_ms)
+    assert stats["steps"] == n * steps
+
+
 @pytest.mark.parametrize("finalize", [True, False])
 @pytest.mark.parametrize("H,W,pieces", [(22, 10, (0, 1, 2, 3, 4, 5, 6)), (16, 8, (0, 6)), (40, 20, (0, 1, 2, 3, 4, 5, 6))])
 def test_world_model_matches_oracle(H, W, pieces, finalize):

@@ -45,6 +45,25 @@ def test_restatement_matches_compiled_reference(kind, H, W, pieces, n, steps, so
         assert stats["lines"] > 0 and stats["garbage"] > 0 and stats["combos"] > 0, stats
 
 
+TIMINGS = [  # kind, time_elapsed_each_action, games, steps: gravity tiers (every > 3000 ms: -10 / -5 / -2 / -1, DropDelay.cpp:3-21),
+    ("greedy", 3100, 4, 420),     # lockdown and garbage / combo timers at other cadences than the default 400 ms
+    ("press_key", 3100, 6, 300),
+    ("press_key", 1000, 6, 300),
+    ("greedy", 50, 4, 200),
+    ("junk", 7, 6, 200),
+]
+
+
+@pytest.mark.parametrize("kind,time_ms,n,steps", TIMINGS)
+def test_other_time_steps_match_compiled_reference(kind, time_ms, n, steps):
+    lead = pyoracle.OracleVector(n)
+    ref = refdrive.RefVector(n)
+    stats = harness.rollout_pair(lead, ref, steps, harness.Policy(kind, kmax=128, lmax=64), time_ms=time_ms, compare_hidden=True)
+    assert stats["steps"] == n * steps
+    if kind == "greedy" and time_ms > 3000:
+        assert int(lead.hidden()[..., 1].min()) < 1000 or stats["dones"] > 0     # the drop delay did shrink
+
+
 def test_rng_streams_match_reference():
     """Piece and hole streams of the restatement vs the compiled reference for edge seeds."""
     for seed in (0, 7, 1000, 32767, 32768, 40000, 65535, 66536, 123456):
