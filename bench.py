@@ -499,6 +499,40 @@ def main():
                                           "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_board": board_bytes(mean_k),
                                           "traffic": ncu_traffic("expand_bytes_per_launch")}}
         w.close()
+        if a.leg == "all":
+            # ---- actor loop: a ply = the world model of every game + the step by the chosen placement, one CUDA-graph launch
+            from b200tetris import ActorLoop
+            al = Engine(nb, H, W, device=local, seed=7 + rank)
+            al.reset_dev(torch.from_numpy((splitmix64(0xA1, bg, 0) & np.uint64(0xFFFF)).astype(np.int64)).to(dev).to(torch.int32))
+            noise = torch.rand(nb * 40, device=dev)
+
+            def score_fn(f, v, p, scores):      # the value network is the consumer's: a fixed pseudo-random score per row stands in
+                scores.copy_(noise)
+            loop = ActorLoop(al, score_fn)
+            for _ in range(24):                  # warm-up plies (capture included): boards fill up, games end and restart
+                loop.step()
+            torch.cuda.synchronize()
+            assert not loop.overflowed()
+            plies = max(4, min(a.steps, 20))
+            rows0 = 0
+            e0.record()
+            for _ in range(plies):
+                loop.step()
+            e1.record()
+            torch.cuda.synchronize()
+            ams = e0.elapsed_time(e1) / plies
+            at = torch.tensor([ams], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(at, op=dist.ReduceOp.MAX)
+            ams = float(at.item())
+            rows = int(loop.offsets[-1].item())
+            out["actor_loop"] = {"env_steps_per_sec": nb * world / (ams * 1e-3), "placements_per_sec": rows * world / (ams * 1e-3),
+                                 "ms_per_ply": ams, "games_per_gpu": nb, "gpu_launches_per_ply": 7, "cuda_graph": True,
+                                 "note": "every ply: enumerate + expand of all placements (uint8 tensors, (me, opponent) order) -> scores "
+                                         "(stand-in: a fixed random tensor; the network is the consumer's) -> select -> step by placement "
+                                         "with engine-chosen reset seeds; no host data, one graph launch (b200tetris.ActorLoop). "
+                                         "SURVEY.md 8d: step + uint8 world model is 14.1 KB per env-step, an HBM ceiling of 4.6e8/s per GPU."}
+            al.close()
         if a.leg == "all" and world == 1:
             # ---- BASELINE configs[4]: custom field sizes and piece sets at 2^18 games
             out["custom_sizes"] = [c5_leg(torch, Engine, dev, local, rank, 16, 8, (0, 6), 1 << 18, 1 << 15, peak, min(a.steps, 10)),

@@ -666,3 +666,53 @@ def test_key_formats_and_engine_chosen_seeds():
         assert episode.max() > 1
         for e in (a, b, c):
             e.close()
+
+
+def test_actor_loop_graph_equals_eager_and_oracle():
+    """b200tetris.ActorLoop: plies replayed as one CUDA graph == the same plies launched eagerly == the oracle driven
+    by the chosen key strings; engine-chosen seeds restart finished games in both."""
+    import torch
+    from b200tetris import ActorLoop, Engine
+    n = 2048
+    dev = torch.device("cuda:0")
+
+    def score_fn(f, v, p, out):      # stand-in for the value network: low, flat stacks of "me" (player axis 0 in perspective order)
+        occ = f[:, 0].to(torch.float32)
+        heights = (occ.cumsum(1) > 0).sum(1).to(torch.float32)            # [rows, W]
+        out.copy_(-heights.sum(1) - 2.0 * (heights[:, 1:] - heights[:, :-1]).abs().sum(1) + 10.0 * (occ.sum((1, 2)) % 10 == 0))
+    seeds = torch.from_numpy(harness.seeds_for(np.arange(n), np.zeros(n, int)).astype(np.int64)).to(dev).to(torch.int32)
+    a, b = Engine(n, seed=99), Engine(n, seed=99)
+    a.reset_dev(seeds); b.reset_dev(seeds)
+    la, lb = ActorLoop(a, score_fn, use_graph=True), ActorLoop(b, score_fn, use_graph=False)
+    sample = np.arange(0, n, 37).astype(np.int32)
+    lead = pyoracle.OracleVector(len(sample))
+    lead.reset(harness.seeds_for(sample, np.zeros(len(sample), int)))
+    alive = np.ones(len(sample), bool)         # sampled games are followed until their first restart (the engine picks that seed)
+    for t in range(60):
+        la.step(); lb.step()
+        torch.cuda.synchronize()
+        assert not la.overflowed()
+        for name in ("K", "choice", "reward", "done", "field", "vec", "piece"):
+            assert torch.equal(getattr(la, name), getattr(lb, name)), (t, name)
+        tot = int(la.offsets[-1].item())
+        assert torch.equal(la.p_field[:tot], lb.p_field[:tot]) and torch.equal(la.scores[:tot], lb.scores[:tot])
+        # the oracle, driven by the key strings the loop chose
+        player = np.full(len(sample), t & 1, np.uint8)
+        Ko, keys_o, klen_o = lead.enumerate(player, kmax=96, lmax=32)[:3]
+        ch = la.choice.cpu().numpy()[sample]
+        assert np.array_equal(Ko[alive], la.K.cpu().numpy()[sample][alive])
+        pick = np.minimum(ch, Ko - 1)
+        ro = lead.step(player, keys_o[np.arange(len(sample)), pick], klen_o[np.arange(len(sample)), pick])
+        assert np.array_equal(ro[0][alive], la.reward.cpu().numpy()[sample][alive]) and np.array_equal(ro[1][alive], la.done.cpu().numpy()[sample][alive])
+        fo = lead.observe()[0]
+        me = 1 - (t & 1)                         # observations come back in the order of the NEXT side to move? no: of the side that moved
+        got = la.field.cpu().numpy()[sample]
+        if t & 1:
+            got = got[:, ::-1]
+        still = alive & ~ro[1].astype(bool)
+        assert np.array_equal(fo[still], got[still]), t
+        alive &= ~ro[1].astype(bool)
+    assert alive.sum() > 0 and la._graph is not None
+    st = a.stats()
+    assert st["env_steps"] == 60 * n and st["capacity_overflow"] == 0
+    a.close(); b.close()
