@@ -180,6 +180,52 @@ def _ref_worker(args):
     return n * steps, time.perf_counter() - t0
 
 
+def _ref_world_model_worker(args):
+    """simulate_all_actions on the compiled reference, raw PythonHandle calls (tetris_environment.py:87-100 without its Python
+    wrappers): per board get_actions, then per placement set(anchor) + make_action + finish_action + copy() (the state object)."""
+    wid, n, plies = args
+    import refmod
+    mod, set_time = refmod.load("B")
+    mod.set_pieces([0, 1, 2, 3, 4, 5, 6])
+    rng = np.random.RandomState(wid)
+    hs = []
+    for g in range(n):
+        set_time(int(splitmix64(0xC3, g + wid * n, 0)) & 0xFFFF)
+        h = mod.PythonHandle(2, [H, W])
+        h.reset()
+        for t in range(plies):                     # a few plies of random placements so the boards are not empty
+            p = (g + t) & 1
+            h.get_actions(p)
+            acts = h.masks[p].action
+            a = [[0], [0]]
+            a[p] = list(acts[rng.randint(len(acts))]) if len(acts) else [0]
+            h.make_action(a)
+            if h.finish_action(400):
+                h.reset()
+        hs.append(h)
+    placements = 0
+    t0 = time.perf_counter()
+    for g, h in enumerate(hs):
+        p = (g + plies) & 1
+        h.get_actions(p)
+        seen, acts = set(), []
+        for k in h.masks[p].action:                # action_list de-duplication (data_types/action_list.py:4-20)
+            k = tuple(k)
+            if k not in seen:
+                seen.add(k); acts.append(list(k))
+        anchor = h.copy()
+        for k in acts:
+            h.set(anchor)
+            a = [[0], [0]]
+            a[p] = k
+            h.make_action(a)
+            h.finish_action(400)
+            h.copy()                               # data_types.state keeps a deep copy of the backend (state.py:5)
+        h.set(anchor)
+        placements += len(acts)
+    return placements, time.perf_counter() - t0
+
+
 def reference_leg(steps, per_proc_games=64, per_proc_steps=40):
     """The reference's own C++ backend (unmodified, compiled -O2 into oracle/_ref/B) on every host core."""
     import multiprocessing as mp
@@ -194,7 +240,16 @@ def reference_leg(steps, per_proc_games=64, per_proc_steps=40):
         for _ in range(max(1, steps)):
             res = pool.map(_ref_worker, [(w, per_proc_games, per_proc_steps) for w in range(cores)])
             vals.append(sum(r[0] for r in res) / max(r[1] for r in res))
+    global _REF_PLACEMENTS
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_ref_world_model_worker, [(w, 24, 16) for w in range(cores)])
+    _REF_PLACEMENTS = {"value": sum(r[0] for r in res) / max(r[1] for r in res), "unit": "placements/s", "cores": cores,
+                       "sample": "%d procs x 24 boards after 16 random plies: get_actions + per placement set/make_action/finish_action/copy "
+                                 "on raw PythonHandle objects" % cores}
     return float(np.median(vals)), cores, "reference", "%d procs x %d games x %d steps of workload S, raw PythonHandle make_action+finish_action loop (no Python front-end, no state copies)" % (cores, per_proc_games, per_proc_steps)
+
+
+_REF_PLACEMENTS = None
 
 
 def c5_leg(torch, Engine, dev, local, rank, h, w, pieces, n, nb, peak, steps):
@@ -293,7 +348,8 @@ def main():
                           "steps": a.steps, "warmup": a.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                           "config": {"workload": "S: SVENton key strings, 2-player 22x10, reset on done; reference CPU backend on host cores"},
-                          "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample},
+                          "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample,
+                                           "placements": _REF_PLACEMENTS},
                           "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
