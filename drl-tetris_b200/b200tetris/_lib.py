@@ -75,6 +75,8 @@ SYMBOLS = {
     "b2t_restore": (C.c_int, [vp, C.c_int32, vp]),
     "b2t_export_state": (C.c_int, [vp, C.c_int32, vp, vp]),
     "b2t_import_state": (C.c_int, [vp, C.c_int32, vp, vp]),
+    "b2t_export_states": (C.c_int, [vp, i32p, C.c_int32, vp]),
+    "b2t_import_states": (C.c_int, [vp, i32p, C.c_int32, vp]),
     "b2t_get_game": (C.c_int, [vp, C.c_int32, C.POINTER(GameRaw), u8p]),
     "b2t_set_game": (C.c_int, [vp, C.c_int32, C.POINTER(GameRaw), u8p]),
     "b2t_copy_game": (C.c_int, [vp, C.c_int32, vp, C.c_int32, vp]),

@@ -195,6 +195,19 @@ class Engine:
         assert buf.size == self.state_bytes
         self._ck(self.lib.b2t_import_state(self._h, int(game), buf.ctypes.data_as(C.c_void_p), None))
 
+    def export_states(self, idx=None):
+        """packed states of the listed games, u8 [n, state_bytes], one call"""
+        idx, n = self._idx(idx)
+        buf = np.empty((n, self.state_bytes), np.uint8)
+        self._ck(self.lib.b2t_export_states(self._h, _hp(idx, C.c_int32), n, buf.ctypes.data_as(C.c_void_p)))
+        return buf
+
+    def import_states(self, buf, idx=None):
+        idx, n = self._idx(idx)
+        buf = np.ascontiguousarray(buf, np.uint8)
+        assert buf.shape == (n, self.state_bytes)
+        self._ck(self.lib.b2t_import_states(self._h, _hp(idx, C.c_int32), n, buf.ctypes.data_as(C.c_void_p)))
+
     def get_game(self, game, want_field=True):
         """b2t_get_game: (GameRaw, field u8[2,H,W] or None) — the game in the reference's own terms"""
         raw = _lib.GameRaw()

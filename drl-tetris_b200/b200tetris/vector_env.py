@@ -45,6 +45,20 @@ class action_list(list):  # environment/data_types/action_list.py:3-37 (the de-d
         super().__init__(action(list(x)) for x in container)
         self.container = self
 
+    @classmethod
+    def from_rows(cls, rows, remove_null):
+        """rows: plain lists of ints straight from the engine's arrays (no per-action type checks: a vector env builds
+        hundreds of thousands of these per call)"""
+        obj = cls.__new__(cls)
+        acts = []
+        for r in rows or [[0]]:
+            a = action.__new__(action)
+            list.__init__(a, r)
+            acts.append(a)
+        list.__init__(obj, acts)
+        obj.remove_null, obj.container = remove_null, obj
+        return obj
+
 
 class reward:  # environment/data_types/reward.py:64-71 maingoal_reward, the subset the env itself uses
     def __init__(self, extrinsic):
@@ -142,8 +156,23 @@ class tetris_environment_vector:
         return [None for _ in ids]
 
     def _lists(self, K, keys, klen):
-        return [action_list([list(map(int, keys[i, k, :klen[i, k]])) for k in range(K[i])], remove_null=self.settings["bar_null_moves"])
-                for i in range(len(K))]
+        """[n, kmax, lmax] key arrays -> one action_list per env; only the valid tokens are turned into Python objects"""
+        n, kmax, lmax = keys.shape
+        rn = self.settings["bar_null_moves"]
+        valid = np.arange(kmax)[None, :] < K[:, None]
+        lens = klen[valid]
+        tok = keys[valid]
+        flat = tok[np.arange(lmax)[None, :] < lens[:, None]].tolist()
+        ends = np.cumsum(lens).tolist()
+        out, a, pos = [], 0, 0
+        for k in K.tolist():
+            rows = []
+            for _ in range(k):
+                e = ends[a]
+                rows.append(flat[pos:e])
+                pos, a = e, a + 1
+            out.append(action_list.from_rows(rows, rn))
+        return out
 
     def get_actions(self, env=None, player=None):  # :60-65 ; tetris_environment.get_actions :77-85
         ids = parse_arg(env, self.envs)
@@ -163,12 +192,12 @@ class tetris_environment_vector:
         assert len(actions) == n and len(pl) == n
         lmax = max(1, max(len(a) for a in actions))
         lmax = (lmax + 15) // 16 * 16
-        keys = np.zeros((n, lmax), np.uint8)
-        klen = np.zeros(n, np.uint8)
-        for j, a in enumerate(actions):
+        for a in actions:
             assert type(a) in (action, list), "tetris_environment.perform_action(action a,int p) was called with type(action)={}".format(type(a))
-            keys[j, :len(a)] = a
-            klen[j] = len(a)
+        klen = np.fromiter(map(len, actions), np.int64, n)
+        keys = np.zeros((n, lmax), np.uint8)
+        keys[np.arange(lmax)[None, :] < klen[:, None]] = np.fromiter((k for a in actions for k in a), np.uint8, int(klen.sum()))
+        klen = klen.astype(np.uint8)
         base, done, _lines, scal = self.engine.step(pl, keys, klen, ids, want_scalars=True)
         rewards = []
         for j, i in enumerate(ids):
@@ -197,7 +226,8 @@ class tetris_environment_vector:
     def get_state(self, env=None):  # :99-101 ; tetris_environment.get_state :131-133
         ids = parse_arg(env, self.envs)
         field, vec, pidx, scal = self.engine.observe(ids, want_scalars=True)
-        return [state(field[j], vec[j], pidx[j], scal[j, :, 7], self.engine.export_state(i)) for j, i in enumerate(ids)]
+        packed = self.engine.export_states(ids)          # one batched copy: the snapshot data_types.state keeps of its backend
+        return [state(field[j], vec[j], pidx[j], scal[j, :, 7], packed[j]) for j in range(len(ids))]
 
     def simulate_all_actions(self, env=None, player=None, finalize=True):  # :93-97 ; tetris_environment :127-129,87-100
         ids = parse_arg(env, self.envs)
@@ -230,8 +260,7 @@ class tetris_environment_vector:
 
     def copy(self):  # :161-167
         other = tetris_environment_vector(self.n_envs, settings=self.settings, device=self.engine.device)
-        for i in self.envs:
-            other.engine.import_state(i, self.engine.export_state(i))
+        other.engine.import_states(self.engine.export_states())
         other.done[:] = self.done
         other._dead[:] = self._dead
         return other

@@ -515,6 +515,33 @@ static int fetch_out(b2t_handle* h, std::vector<Out*> outs, cudaStream_t s) {
     return B2T_OK;
 }
 
+int b2t_export_states(b2t_handle* h, const int32_t* h_idx, int32_t n, void* h_buf) {
+    if (!h || !h_buf || n < 0 || n > h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_export_states: bad argument%s");
+    if (!n) return B2T_OK;
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t bytes = (size_t)n * h->ops->NV * 16;
+    In idx; idx.src = h_idx; idx.bytes = (size_t)n * 4;
+    if (int r = stage_in(h, {&idx}, 0)) return r;
+    Out buf; buf.dst = h_buf; buf.bytes = bytes;
+    if (int r = plan_out(h, {&buf})) return r;
+    const long long t = (long long)n * h->ops->NV;
+    gather_games_kernel<<<(unsigned)((t + 255) / 256), 256>>>(h->state, (const int32_t*)dev_in(h->in, idx), n, h->ops->NV, (uint4*)dev_out(h->out, buf));
+    CK(cudaGetLastError());
+    return fetch_out(h, {&buf}, 0);
+}
+int b2t_import_states(b2t_handle* h, const int32_t* h_idx, int32_t n, const void* h_buf) {
+    if (!h || !h_buf || n < 0 || n > h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_import_states: bad argument%s");
+    if (!n) return B2T_OK;
+    CK(cudaSetDevice(h->cfg.device));
+    In idx, buf; idx.src = h_idx; idx.bytes = (size_t)n * 4; buf.src = h_buf; buf.bytes = (size_t)n * h->ops->NV * 16;
+    if (int r = stage_in(h, {&idx, &buf}, 0)) return r;
+    const long long t = (long long)n * h->ops->NV;
+    scatter_games_kernel<<<(unsigned)((t + 255) / 256), 256>>>(h->state, (const int32_t*)dev_in(h->in, idx), n, h->ops->NV, (const uint4*)dev_in(h->in, buf));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(0));
+    return B2T_OK;
+}
+
 int b2t_reset_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint32_t* h_seeds) {
     if (!h) return B2T_ERR_ARG;
     if (n < 0 || n > h->cfg.n_games || !h_seeds) return fail(h, B2T_ERR_ARG, "b2t_reset_host: bad n or NULL seeds%s");

@@ -1068,6 +1068,19 @@ __global__ void copy_tiles_kernel(uint32_t* dst_tiles, int dst, const uint32_t* 
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w < nw) dst_tiles[((size_t)(dst >> 5) * nw + w) * 32 + (dst & 31)] = src_tiles ? src_tiles[((size_t)(src >> 5) * nw + w) * 32 + (src & 31)] : 0u;
 }
+// n games' vectors <-> one contiguous buffer [n][nv] (batched export / import: get_state of a whole vector of envs)
+__global__ void gather_games_kernel(const uint4* state, const int32_t* idx, int n, int nv, uint4* out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n * nv) return;
+    const int i = (int)(t / nv), v = (int)(t % nv), game = idx ? idx[i] : i;
+    out[t] = state[((size_t)(game >> 5) * nv + v) * 32 + (game & 31)];
+}
+__global__ void scatter_games_kernel(uint4* state, const int32_t* idx, int n, int nv, const uint4* in) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n * nv) return;
+    const int i = (int)(t / nv), v = (int)(t % nv), game = idx ? idx[i] : i;
+    state[((size_t)(game >> 5) * nv + v) * 32 + (game & 31)] = in[t];
+}
 // PythonHandle.copy()/set() of one game, possibly between two handles of the same field size
 __global__ void copy_game_kernel(uint4* dst_state, int dst, const uint4* src_state, int src, int nv) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;

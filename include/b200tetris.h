@@ -181,6 +181,11 @@ int b2t_restore(b2t_handle *h, int32_t slot, void *stream);
 int b2t_export_state(b2t_handle *h, int32_t game, void *h_buf, void *stream);
 int b2t_import_state(b2t_handle *h, int32_t game, const void *h_buf, void *stream);
 
+/* The same for n games in one call (get_state / set of a whole vector of envs): h_buf is [n][state_bytes]; h_game_idx NULL =
+ * games 0..n-1.  Synchronise. */
+int b2t_export_states(b2t_handle *h, const int32_t *h_game_idx, int32_t n, void *h_buf);
+int b2t_import_states(b2t_handle *h, const int32_t *h_game_idx, int32_t n, const void *h_buf);
+
 /* ---- one game in the reference's own terms: what PythonHandle.states[p] shows (PythonHandle.h:54-82) plus the hidden
  * members its pickle support walks (PythonHandle.h:207-308).  This is the exchange format of the per-env compatibility
  * facade (b200tetris/tetris_env.py: a PythonHandle-shaped object per game slot), of pickling, and of white-box tests. */

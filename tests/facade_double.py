@@ -55,6 +55,13 @@ class HostSimEngine:
             out[name] = np.concatenate([o[name][i, :K[i]] for i in range(len(K))]) if len(K) else o[name][:0, 0]
         return out
 
+    def export_states(self, idx=None):
+        return [self.export_state(i) for i in (range(self.n) if idx is None else idx)]
+
+    def import_states(self, bufs, idx=None):
+        for i, b in zip(range(self.n) if idx is None else idx, bufs):
+            self.import_state(i, b)
+
     def export_state(self, game):
         raw, field = self.v.get_game(game)
         return (bytes(raw), field.tobytes())
