@@ -544,11 +544,18 @@ def main():
         if world > 1:
             dist.all_reduce(pt, op=dist.ReduceOp.MAX)
         ms = float(pt.item())
+        e0.record()
+        for _ in range(reps):
+            expand(False)                      # Sherlock's mode (sherlock_utils.py:14): pieces locked, nothing finished
+        e1.record()
+        torch.cuda.synchronize()
+        ms_nf = e0.elapsed_time(e1) / reps
         mean_k = total / nb
         ach = board_bytes(mean_k) * nb / (ms * 1e-3) / 1e9
         out["placements"] = {"metric": "placements_per_sec", "value": total * world / (ms * 1e-3), "unit": "placements/s",
                              "boards_per_sec": nb * world / (ms * 1e-3), "boards_per_gpu": nb, "mean_K": mean_k, "ms_per_expand": ms,
-                             "finalize": True, "gpu_launches_per_expand": 5,
+                             "finalize": True, "gpu_launches_per_expand": 6,
+                             "finalize_false": {"value": total * world / (ms_nf * 1e-3), "ms_per_expand": ms_nf},
                              "workload": "C3 (BASELINE configs[2]): %d boards after 8..40 plies of random placements; enumerate + scan + "
                                          "expand(finalize=1) with uint8 tensors, keys, reward, done for every placement" % nb,
                              "roofline": {"bound": "hbm", "kernel": "enumerate_kernel + game_kernel<22,10> (expand)", "achieved": ach, "peak": peak,
