@@ -670,49 +670,63 @@ def test_key_formats_and_engine_chosen_seeds():
 
 def test_actor_loop_graph_equals_eager_and_oracle():
     """b200tetris.ActorLoop: plies replayed as one CUDA graph == the same plies launched eagerly == the oracle driven
-    by the chosen key strings; engine-chosen seeds restart finished games in both."""
+    by the chosen key strings, through line clears, garbage, combos and restarts (the engine-chosen seeds are a known counter hash)."""
     import torch
     from b200tetris import ActorLoop, Engine
-    n = 2048
+    n, plies, base = 2048, 240, 99
     dev = torch.device("cuda:0")
 
-    def score_fn(f, v, p, out):      # stand-in for the value network: low, flat stacks of "me" (player axis 0 in perspective order)
+    def score_fn(f, v, p, out):      # stand-in for the value network: low, flat, hole-free stacks of "me" (player axis 0 in perspective order)
         occ = f[:, 0].to(torch.float32)
-        heights = (occ.cumsum(1) > 0).sum(1).to(torch.float32)            # [rows, W]
-        out.copy_(-heights.sum(1) - 2.0 * (heights[:, 1:] - heights[:, :-1]).abs().sum(1) + 10.0 * (occ.sum((1, 2)) % 10 == 0))
+        filled_above = (occ.cumsum(1) > 0).to(torch.float32)
+        heights = filled_above.sum(1)                                       # [rows, W]
+        holes = (filled_above - occ).sum((1, 2))
+        out.copy_(-0.5 * heights.sum(1) - 0.4 * (heights[:, 1:] - heights[:, :-1]).abs().sum(1) - 5.0 * holes)
+
+    def auto_seed(game, episode):
+        z = (base + game * 0x9E3779B1 + episode * 0x85EBCA77) & 0xFFFFFFFF
+        z ^= z >> 15; z = (z * 0x2C1B3C6D) & 0xFFFFFFFF; z ^= z >> 12; z = (z * 0x297A2D39) & 0xFFFFFFFF; z ^= z >> 15
+        return z & 0xFFFF
     seeds = torch.from_numpy(harness.seeds_for(np.arange(n), np.zeros(n, int)).astype(np.int64)).to(dev).to(torch.int32)
-    a, b = Engine(n, seed=99), Engine(n, seed=99)
+    a, b = Engine(n, seed=base), Engine(n, seed=base)
     a.reset_dev(seeds); b.reset_dev(seeds)
     la, lb = ActorLoop(a, score_fn, use_graph=True), ActorLoop(b, score_fn, use_graph=False)
     sample = np.arange(0, n, 37).astype(np.int32)
-    lead = pyoracle.OracleVector(len(sample))
-    lead.reset(harness.seeds_for(sample, np.zeros(len(sample), int)))
-    alive = np.ones(len(sample), bool)         # sampled games are followed until their first restart (the engine picks that seed)
-    for t in range(60):
+    m = len(sample)
+    lead = pyoracle.OracleVector(m)
+    lead.reset(harness.seeds_for(sample, np.zeros(m, int)))
+    episode = np.ones(m, np.int64)
+    lines = garbage = restarts = 0
+    for t in range(plies):
         la.step(); lb.step()
         torch.cuda.synchronize()
         assert not la.overflowed()
-        for name in ("K", "choice", "reward", "done", "field", "vec", "piece"):
-            assert torch.equal(getattr(la, name), getattr(lb, name)), (t, name)
-        tot = int(la.offsets[-1].item())
-        assert torch.equal(la.p_field[:tot], lb.p_field[:tot]) and torch.equal(la.scores[:tot], lb.scores[:tot])
+        if t % 8 == 0 or t < 4:
+            for name in ("K", "choice", "reward", "done", "field", "vec", "piece"):
+                assert torch.equal(getattr(la, name), getattr(lb, name)), (t, name)
+            tot = int(la.offsets[-1].item())
+            assert torch.equal(la.p_field[:tot], lb.p_field[:tot]) and torch.equal(la.scores[:tot], lb.scores[:tot])
         # the oracle, driven by the key strings the loop chose
-        player = np.full(len(sample), t & 1, np.uint8)
+        player = np.full(m, t & 1, np.uint8)
         Ko, keys_o, klen_o = lead.enumerate(player, kmax=96, lmax=32)[:3]
+        assert np.array_equal(Ko, la.K.cpu().numpy()[sample]), t
         ch = la.choice.cpu().numpy()[sample]
-        assert np.array_equal(Ko[alive], la.K.cpu().numpy()[sample][alive])
-        pick = np.minimum(ch, Ko - 1)
-        ro = lead.step(player, keys_o[np.arange(len(sample)), pick], klen_o[np.arange(len(sample)), pick])
-        assert np.array_equal(ro[0][alive], la.reward.cpu().numpy()[sample][alive]) and np.array_equal(ro[1][alive], la.done.cpu().numpy()[sample][alive])
-        fo = lead.observe()[0]
-        me = 1 - (t & 1)                         # observations come back in the order of the NEXT side to move? no: of the side that moved
-        got = la.field.cpu().numpy()[sample]
-        if t & 1:
-            got = got[:, ::-1]
-        still = alive & ~ro[1].astype(bool)
-        assert np.array_equal(fo[still], got[still]), t
-        alive &= ~ro[1].astype(bool)
-    assert alive.sum() > 0 and la._graph is not None
+        ro = lead.step(player, keys_o[np.arange(m), ch], klen_o[np.arange(m), ch])
+        assert np.array_equal(ro[0], la.reward.cpu().numpy()[sample]) and np.array_equal(ro[1], la.done.cpu().numpy()[sample]), t
+        ended = np.nonzero(ro[1])[0]
+        if len(ended):                           # the fused reset used auto_seed(cfg.seed, game, rounds started)
+            lead.reset(np.array([auto_seed(int(sample[i]), int(episode[i])) for i in ended], np.uint32), ended.astype(np.int32))
+            episode[ended] += 1
+            restarts += len(ended)
+        fo, vo, _ = lead.observe()
+        got_f, got_v = la.field.cpu().numpy()[sample], la.vec.cpu().numpy()[sample]
+        if t & 1:                                # perspective order of the side that moved
+            got_f, got_v = got_f[:, ::-1], got_v[:, ::-1]
+        assert np.array_equal(fo, got_f), t
+        if t > 0:
+            assert np.array_equal(vo, got_v), t
+        lines += int(ro[2].sum()); garbage += int((vo[..., 2] > 0).sum())
+    assert lines > 0 and garbage > 0 and restarts > 0 and la._graph is not None, (lines, garbage, restarts)
     st = a.stats()
-    assert st["env_steps"] == 60 * n and st["capacity_overflow"] == 0
+    assert st["env_steps"] == plies * n and st["capacity_overflow"] == 0 and st["garbage_queue_overflow"] == 0
     a.close(); b.close()
