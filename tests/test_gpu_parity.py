@@ -730,3 +730,39 @@ def test_actor_loop_graph_equals_eager_and_oracle():
     st = a.stats()
     assert st["env_steps"] == plies * n and st["capacity_overflow"] == 0 and st["garbage_queue_overflow"] == 0
     a.close(); b.close()
+
+
+def test_sliced_host_step_with_a_game_subset():
+    """b2t_step_host slices batches of >= 65 536 rows over two streams: a permuted 70 000-game subset given by index, with
+    observations and scalars copied back, equals the unsliced device-pointer step of a twin engine."""
+    import torch
+    from b200tetris import Engine
+    n, m = 1 << 17, 70000
+    dev = torch.device("cuda:0")
+    a, b = Engine(n), Engine(n)
+    seeds = harness.seeds_for(np.arange(n), np.zeros(n, int))
+    a.reset(seeds); b.reset(seeds)
+    rng = np.random.default_rng(3)
+    pol = harness.Policy("sventon", lmax=16)
+
+    class L:
+        W = 10
+    for t in range(6):
+        idx = rng.permutation(n)[:m].astype(np.int32)
+        player = ((idx + t) & 1).astype(np.uint8)
+        keys, klen, _ = pol.choose(L, t, idx, player)
+        rs = harness.seeds_for(idx, np.full(m, t + 1))
+        ra = a.step(player, keys, klen, idx, reset_seeds=rs, want_obs=True, want_scalars=True)
+        f = torch.empty((m, 2, 22, 10), dtype=torch.uint8, device=dev); v = torch.empty((m, 2, 19), dtype=torch.uint8, device=dev)
+        pi = torch.empty((m, 2), dtype=torch.uint8, device=dev); sc = torch.empty((m, 2, 8), dtype=torch.int32, device=dev)
+        rw = torch.empty(m, dtype=torch.int8, device=dev); dn = torch.empty(m, dtype=torch.uint8, device=dev); ln = torch.empty((m, 2), dtype=torch.uint8, device=dev)
+        b.step_dev(torch.from_numpy(player).to(dev), torch.from_numpy(keys).to(dev), torch.from_numpy(klen).to(dev), idx=torch.from_numpy(idx).to(dev),
+                   reset_seeds=torch.from_numpy(rs.astype(np.int64)).to(dev).to(torch.int32), reward=rw, done=dn, lines=ln, field=f, vec=v, piece_idx=pi, scalars=sc)
+        torch.cuda.synchronize()
+        for x, y in zip(ra[:3], (rw, dn, ln)):
+            assert np.array_equal(x, y.cpu().numpy()), t
+        for x, y in zip(ra[3], (f, v, pi)):
+            assert np.array_equal(x, y.cpu().numpy()), t
+        assert np.array_equal(ra[4], sc.cpu().numpy()), t
+    assert np.array_equal(a.export_states(), b.export_states())
+    a.close(); b.close()
