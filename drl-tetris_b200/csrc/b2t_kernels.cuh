@@ -585,11 +585,16 @@ __global__ void __launch_bounds__(TPB, MODE == GM_EXPAND ? B2T_GAME_MINB + 1 : B
     }
     // ---- episode statistics: one atomic per non-zero counter per warp, spread over slices
     if (p.stats && (flags & KF_STEP)) {
-        int vals[STAT_WORDS] = {st_steps, st_done, st_w0, st_w1, st_both, st_lines, st_gq, st_rng};
+        // the eight per-lane contributions are tiny (flags, or <= 8 lines): two packed warp reductions instead of eight
+        const uint32_t pa = (uint32_t)st_steps | ((uint32_t)st_done << 6) | ((uint32_t)st_w0 << 12) | ((uint32_t)st_w1 << 18) | ((uint32_t)st_both << 24);
+        const uint32_t pb = (uint32_t)st_lines | ((uint32_t)st_gq << 10) | ((uint32_t)st_rng << 16);
+        const uint32_t ra = __reduce_add_sync(0xFFFFFFFFu, pa), rb = __reduce_add_sync(0xFFFFFFFFu, pb);
+        if (lane == 0) {
+            const uint32_t vals[STAT_WORDS] = {ra & 63u, (ra >> 6) & 63u, (ra >> 12) & 63u, (ra >> 18) & 63u, (ra >> 24) & 63u,
+                                               rb & 1023u, (rb >> 10) & 63u, (rb >> 16) & 63u};
 #pragma unroll
-        for (int j = 0; j < STAT_WORDS; j++) {
-            const int s = __reduce_add_sync(0xFFFFFFFFu, vals[j]);
-            if (lane == 0 && s) atomicAdd(&p.stats[(blockIdx.x % STAT_SLICES) * STAT_WORDS + j], (unsigned long long)s);
+            for (int j = 0; j < STAT_WORDS; j++)
+                if (vals[j]) atomicAdd(&p.stats[(blockIdx.x % STAT_SLICES) * STAT_WORDS + j], (unsigned long long)vals[j]);
         }
     }
 }
