@@ -10,7 +10,8 @@
  *   - pointers named d_* are DEVICE pointers on the handle's device, 16-byte aligned; pointers named h_* are HOST
  *     pointers.  The library never takes ownership of caller memory.
  *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Device-pointer calls are asynchronous;
- *     *_host calls synchronise before returning.
+ *     *_host calls run on the legacy default stream (plus two internal streams for large batches) and synchronise before
+ *     returning; a caller that also drives the handle from non-blocking streams of its own orders the two itself.
  *   - game_idx == NULL means "games 0..n-1"; otherwise n distinct game ids (duplicates in one call are undefined,
  *     like stepping one PythonHandle from two threads).
  *   - a handle is not thread-safe (neither is the reference); handles on different devices are independent.
