@@ -478,6 +478,7 @@ static void* dev_out(const Arena& a, const Out& o) { return o.dst ? a.d + o.off 
 
 // Pinned (cudaMallocHost / cudaHostRegister'ed, e.g. torch pin_memory) caller buffers are copied straight to / from the
 // device arena; pageable ones go through the handle's pinned staging (one extra host memcpy).
+constexpr size_t DIRECT_COPY_MIN = 1 << 16;   // smaller arrays go through the handle's pinned staging without asking the driver
 static bool is_pinned(const void* p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -491,7 +492,7 @@ static int stage_in(b2t_handle* h, std::vector<In*> ins, cudaStream_t s) {
         if (!i->src || !i->bytes) { if (i->src) i->off = h->in.take(1); continue; }
         i->off = h->in.take(i->bytes);
         const void* from = i->src;
-        if (!is_pinned(from)) { memcpy(h->in.h + i->off, i->src, i->bytes); from = h->in.h + i->off; }
+        if (i->bytes < DIRECT_COPY_MIN || !is_pinned(from)) { memcpy(h->in.h + i->off, i->src, i->bytes); from = h->in.h + i->off; }
         CK(cudaMemcpyAsync(h->in.d + i->off, from, i->bytes, cudaMemcpyHostToDevice, s));
     }
     return B2T_OK;
@@ -507,7 +508,7 @@ static int fetch_out(b2t_handle* h, std::vector<Out*> outs, cudaStream_t s) {
     std::vector<Out*> staged;
     for (auto o : outs) {
         if (!o->dst || !o->bytes) continue;
-        if (is_pinned(o->dst)) CK(cudaMemcpyAsync(o->dst, h->out.d + o->off, o->bytes, cudaMemcpyDeviceToHost, s));
+        if (o->bytes >= DIRECT_COPY_MIN && is_pinned(o->dst)) CK(cudaMemcpyAsync(o->dst, h->out.d + o->off, o->bytes, cudaMemcpyDeviceToHost, s));
         else { CK(cudaMemcpyAsync(h->out.h + o->off, h->out.d + o->off, o->bytes, cudaMemcpyDeviceToHost, s)); staged.push_back(o); }
     }
     CK(cudaStreamSynchronize(s));
