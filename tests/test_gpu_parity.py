@@ -673,7 +673,7 @@ def test_actor_loop_graph_equals_eager_and_oracle():
     by the chosen key strings, through line clears, garbage, combos and restarts (the engine-chosen seeds are a known counter hash)."""
     import torch
     from b200tetris import ActorLoop, Engine
-    n, plies, base = 2048, 240, 99
+    n, plies, base = int(os.environ.get("B2T_SOAK_N", 2048)), int(os.environ.get("B2T_SOAK_PLIES", 240)), 99   # env: a longer soak by hand
     dev = torch.device("cuda:0")
 
     def score_fn(f, v, p, out):      # stand-in for the value network: low, flat, hole-free stacks of "me" (player axis 0 in perspective order)
@@ -691,7 +691,7 @@ def test_actor_loop_graph_equals_eager_and_oracle():
     a, b = Engine(n, seed=base), Engine(n, seed=base)
     a.reset_dev(seeds); b.reset_dev(seeds)
     la, lb = ActorLoop(a, score_fn, use_graph=True), ActorLoop(b, score_fn, use_graph=False)
-    sample = np.arange(0, n, 37).astype(np.int32)
+    sample = np.arange(0, n, max(37, n // 96)).astype(np.int32)
     m = len(sample)
     lead = pyoracle.OracleVector(m)
     lead.reset(harness.seeds_for(sample, np.zeros(m, int)))
@@ -727,6 +727,7 @@ def test_actor_loop_graph_equals_eager_and_oracle():
             assert np.array_equal(vo, got_v), t
         lines += int(ro[2].sum()); garbage += int((vo[..., 2] > 0).sum())
     assert lines > 0 and garbage > 0 and restarts > 0 and la._graph is not None, (lines, garbage, restarts)
+    print("actor-loop soak: %d games x %d plies, %d sampled games vs oracle: lines %d, garbage observations %d, restarts %d" % (n, plies, m, lines, garbage, restarts))
     st = a.stats()
     assert st["env_steps"] == plies * n and st["capacity_overflow"] == 0 and st["garbage_queue_overflow"] == 0
     a.close(); b.close()
