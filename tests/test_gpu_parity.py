@@ -668,12 +668,14 @@ def test_key_formats_and_engine_chosen_seeds():
             e.close()
 
 
-def test_actor_loop_graph_equals_eager_and_oracle():
+@pytest.mark.parametrize("H,W,pieces,n0,plies0", [(22, 10, ALL7, 2048, 240), (16, 8, (0, 6), 1024, 200), (40, 20, ALL7, 256, 120)])
+def test_actor_loop_graph_equals_eager_and_oracle(H, W, pieces, n0, plies0):
     """b200tetris.ActorLoop: plies replayed as one CUDA graph == the same plies launched eagerly == the oracle driven
     by the chosen key strings, through line clears, garbage, combos and restarts (the engine-chosen seeds are a known counter hash)."""
     import torch
     from b200tetris import ActorLoop, Engine
-    n, plies, base = int(os.environ.get("B2T_SOAK_N", 2048)), int(os.environ.get("B2T_SOAK_PLIES", 240)), 99   # env: a longer soak by hand
+    n, plies, base = int(os.environ.get("B2T_SOAK_N", n0)), int(os.environ.get("B2T_SOAK_PLIES", plies0)), 99   # env: a longer soak by hand
+    okmax, olmax = (256, 128) if W > 10 else (96, 64)
     dev = torch.device("cuda:0")
 
     def score_fn(f, v, p, out):      # stand-in for the value network: low, flat, hole-free stacks of "me" (player axis 0 in perspective order)
@@ -688,12 +690,13 @@ def test_actor_loop_graph_equals_eager_and_oracle():
         z ^= z >> 15; z = (z * 0x2C1B3C6D) & 0xFFFFFFFF; z ^= z >> 12; z = (z * 0x297A2D39) & 0xFFFFFFFF; z ^= z >> 15
         return z & 0xFFFF
     seeds = torch.from_numpy(harness.seeds_for(np.arange(n), np.zeros(n, int)).astype(np.int64)).to(dev).to(torch.int32)
-    a, b = Engine(n, seed=base), Engine(n, seed=base)
+    a, b = Engine(n, H, W, pieces, seed=base), Engine(n, H, W, pieces, seed=base)
     a.reset_dev(seeds); b.reset_dev(seeds)
-    la, lb = ActorLoop(a, score_fn, use_graph=True), ActorLoop(b, score_fn, use_graph=False)
+    rpg = 40 if W <= 10 else 120
+    la, lb = ActorLoop(a, score_fn, rows_per_game=rpg, use_graph=True), ActorLoop(b, score_fn, rows_per_game=rpg, use_graph=False)
     sample = np.arange(0, n, max(37, n // 96)).astype(np.int32)
     m = len(sample)
-    lead = pyoracle.OracleVector(m)
+    lead = pyoracle.OracleVector(m, H, W, pieces)
     lead.reset(harness.seeds_for(sample, np.zeros(m, int)))
     episode = np.ones(m, np.int64)
     lines = garbage = restarts = 0
@@ -708,7 +711,7 @@ def test_actor_loop_graph_equals_eager_and_oracle():
             assert torch.equal(la.p_field[:tot], lb.p_field[:tot]) and torch.equal(la.scores[:tot], lb.scores[:tot])
         # the oracle, driven by the key strings the loop chose
         player = np.full(m, t & 1, np.uint8)
-        Ko, keys_o, klen_o = lead.enumerate(player, kmax=96, lmax=32)[:3]
+        Ko, keys_o, klen_o = lead.enumerate(player, kmax=okmax, lmax=olmax)[:3]
         assert np.array_equal(Ko, la.K.cpu().numpy()[sample]), t
         ch = la.choice.cpu().numpy()[sample]
         ro = lead.step(player, keys_o[np.arange(m), ch], klen_o[np.arange(m), ch])
@@ -726,7 +729,7 @@ def test_actor_loop_graph_equals_eager_and_oracle():
         if t > 0:
             assert np.array_equal(vo, got_v), t
         lines += int(ro[2].sum()); garbage += int((vo[..., 2] > 0).sum())
-    assert lines > 0 and garbage > 0 and restarts > 0 and la._graph is not None, (lines, garbage, restarts)
+    assert la._graph is not None and (W > 10 or (lines > 0 and garbage > 0 and restarts > 0)), (lines, garbage, restarts)
     print("actor-loop soak: %d games x %d plies, %d sampled games vs oracle: lines %d, garbage observations %d, restarts %d" % (n, plies, m, lines, garbage, restarts))
     st = a.stats()
     assert st["env_steps"] == plies * n and st["capacity_overflow"] == 0 and st["garbage_queue_overflow"] == 0
