@@ -57,7 +57,7 @@ class PlayerRaw(C.Structure):   # b2t_player_raw
 
 class GameRaw(C.Structure):     # b2t_game_raw
     _fields_ = [("seed16", C.c_int32), ("round_over", C.c_int32), ("done", C.c_int32), ("last_winner", C.c_int32),
-                ("overflow", C.c_int32), ("player", PlayerRaw * 2)]
+                ("overflow", C.c_int32), ("rounds_started", C.c_int32), ("player", PlayerRaw * 2)]
 
 
 SYMBOLS = {

@@ -49,6 +49,7 @@ template <class G> void decode_game(const uint32_t* words, b2t_game_raw* out, ui
     out->round_over = (gf & GF_ROUND_OVER) ? 1 : 0;
     out->done = (gf & GF_ENV_DONE) ? 1 : 0;
     out->last_winner = ((gf >> GF_WINNER_SHIFT) & 3) - 1;
+    out->rounds_started = (int32_t)hg.g.p[0].episode;
     for (int p = 0; p < 2; p++) {
         const PS& s = hg.g.p[p];
         b2t_player_raw& r = out->player[p];
@@ -121,6 +122,8 @@ template <class G> void encode_game(uint32_t* words, const b2t_game_raw* in, con
         }
     }
     hg.g.p[0].hi12 = (uint32_t)in->seed16 & 0xFFFFu;
+    hg.g.p[0].episode = (uint32_t)in->rounds_started & 0xFFFFu;
+    hg.g.p[1].episode = 0;
     hg.g.set_gf(gf);
     hg.store(words);
 }

@@ -221,6 +221,7 @@ typedef struct {
     int32_t done;               /* tetris_environment.done as maintained by b2t_step */
     int32_t last_winner;        /* PythonHandle::last_winner */
     int32_t overflow;           /* bit 0: garbage queue outgrew 6 entries, bit 1: a stream table was outrun */
+    int32_t rounds_started;     /* resets so far (mod 65536): the counter behind engine-chosen round seeds (auto_reset) */
     b2t_player_raw player[2];
 } b2t_game_raw;
 

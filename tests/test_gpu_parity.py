@@ -770,3 +770,27 @@ def test_sliced_host_step_with_a_game_subset():
         assert np.array_equal(ra[4], sc.cpu().numpy()), t
     assert np.array_equal(a.export_states(), b.export_states())
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("H,W,pieces", [(22, 10, ALL7), (40, 20, ALL7), (12, 5, (4,))])
+def test_game_codec_round_trip(H, W, pieces):
+    """b2t_get_game -> b2t_set_game into another slot reproduces the packed state word for word (the raw form is complete:
+    pickling and per-env copies through the host lose nothing), after play with garbage, combos, restarts."""
+    from b200tetris import Engine
+    n = 64
+    e = Engine(2 * n, H, W, pieces, seed=5)
+    gids = np.arange(n)
+    e.reset(harness.seeds_for(gids, np.zeros(n, int)), gids)
+    rng = np.random.default_rng(1)
+    for t in range(90):
+        player = ((gids + t) & 1).astype(np.uint8)
+        K, keys, klen = e.enumerate(player, gids)
+        sel = rng.integers(0, 1 << 30, n) % K
+        e.step(player, keys[gids, sel], klen[gids, sel], gids, auto_reset=True, time_ms=int(rng.choice([400, 1000, 3100])))
+        if t % 30 == 29:
+            for g in range(0, n, 3):
+                raw, field = e.get_game(g)
+                e.set_game(n + g, raw, field)
+            a, b = e.export_states(gids[::3]), e.export_states(n + gids[::3])
+            assert np.array_equal(a, b), np.argwhere(a != b)[:5]
+    e.close()
