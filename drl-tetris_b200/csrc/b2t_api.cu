@@ -572,6 +572,39 @@ int b2t_step_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint8_t*
     rew.dst = h_reward; rew.bytes = N; done.dst = h_done; done.bytes = N; lines.dst = h_lines; lines.bytes = 2 * N;
     field.dst = h_field; field.bytes = 2 * HW * N; vec.dst = h_vec; vec.bytes = 2 * B2T_VEC_LEN * N;
     pidx.dst = h_piece_idx; pidx.bytes = 2 * N; scal.dst = h_scalars; scal.bytes = 64 * N;
+    {
+        // Large batch, every buffer pinned, no observation tensors asked for: the kernel reads the keys and writes reward / done /
+        // lines straight through the caller's pinned pages (they are device-addressable under unified addressing), so the
+        // PCIe traffic overlaps the compute inside ONE launch instead of being copies before and after it.
+        static const bool zero_copy = !(getenv("B2T_ZERO_COPY") && atoi(getenv("B2T_ZERO_COPY")) == 0);
+        auto mapped = [](const void* p) -> void* {
+            if (!p) return nullptr;
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+        };
+        if (zero_copy && n >= PIPE_MIN_ROWS && !h_field && !h_vec && !h_piece_idx && !h_scalars) {
+            const void* ins_h[6] = {h_idx, h_player, h_keys, h_key_len, h_placement, h_reset_seeds};
+            void* outs_h[3] = {h_reward, h_done, h_lines};
+            void* ins_d[6];
+            void* outs_d[3];
+            bool ok = true;
+            for (int k = 0; k < 6; k++) { ins_d[k] = mapped(ins_h[k]); ok = ok && (!ins_h[k] || ins_d[k]); }
+            for (int k = 0; k < 3; k++) { outs_d[k] = mapped(outs_h[k]); ok = ok && (!outs_h[k] || outs_d[k]); }
+            if (ok) {
+                b2t_step_args a;
+                memset(&a, 0, sizeof a);
+                a.d_game_idx = (const int32_t*)ins_d[0]; a.n = n; a.d_player = (const uint8_t*)ins_d[1];
+                a.d_keys = (const uint8_t*)ins_d[2]; a.d_key_len = (const uint8_t*)ins_d[3]; a.lmax = lmax;
+                a.d_placement = (const int32_t*)ins_d[4]; a.finalize = finalize; a.time_ms = time_ms;
+                a.d_reset_seeds = (const uint32_t*)ins_d[5]; a.key_format = key_format; a.auto_reset = auto_reset;
+                a.d_reward = (int8_t*)outs_d[0]; a.d_done = (uint8_t*)outs_d[1]; a.d_lines = (uint8_t*)outs_d[2];
+                if (int r = step_launch(h, &a, 0, nullptr)) return r;
+                CK(cudaStreamSynchronize(0));
+                return B2T_OK;
+            }
+        }
+    }
     if (n >= PIPE_MIN_ROWS) {
         // Large batch: slices of the rows go down, through the kernel and back up on two streams, so the PCIe copies of one
         // slice overlap the kernel of another (a step of 2^20 games is 23 MB in, 0.25 ms of kernel, 4 MB out).

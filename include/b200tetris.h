@@ -243,7 +243,9 @@ int b2t_clear_field(b2t_handle *h, int32_t game, int32_t player, void *stream);
 int b2t_stats(b2t_handle *h, uint64_t *h_out, void *stream);
 
 /* ---- host-buffer entry points (what a ctypes / pybind11 shim that owns numpy arrays calls) ----
- * Same semantics as above with HOST pointers; copies go through pinned staging owned by the handle. */
+ * Same semantics as above with HOST pointers.  Pageable buffers are copied through pinned staging owned by the handle, pinned
+ * ones directly; b2t_step_host of a large batch (>= 65 536 rows) whose buffers are ALL pinned and that asks for no observation
+ * tensors copies nothing: the kernel reads and writes the caller's pinned pages (zero-copy). */
 int b2t_reset_host(b2t_handle *h, const int32_t *h_game_idx, int32_t n, const uint32_t *h_seeds);
 int b2t_step_host(b2t_handle *h, const int32_t *h_game_idx, int32_t n, const uint8_t *h_player, const uint8_t *h_keys,
                   const uint8_t *h_key_len, int32_t lmax, const int32_t *h_placement, int32_t finalize, int32_t time_ms,

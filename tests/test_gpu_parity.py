@@ -768,6 +768,29 @@ def test_sliced_host_step_with_a_game_subset():
         for x, y in zip(ra[3], (f, v, pi)):
             assert np.array_equal(x, y.cpu().numpy()), t
         assert np.array_equal(ra[4], sc.cpu().numpy()), t
+    # the zero-copy form of the same call: every buffer pinned (b2t_host_alloc), no observation tensors -> the kernel reads the
+    # keys and writes reward / done / lines through the caller's pages
+    import ctypes as C
+    from b200tetris import host_array
+    from b200tetris.engine import _hp
+    for t in range(6, 10):
+        idx = rng.permutation(n)[:m].astype(np.int32)
+        player = ((idx + t) & 1).astype(np.uint8)
+        keys, klen, _ = pol.choose(L, t, idx, player)
+        rs = harness.seeds_for(idx, np.full(m, t + 1))
+        hp = {k: host_array(v.shape, v.dtype, write_combined=(k != "idx")) for k, v in (("idx", idx), ("player", player), ("keys", keys), ("klen", klen), ("rs", rs))}
+        for k, v in (("idx", idx), ("player", player), ("keys", keys), ("klen", klen), ("rs", rs)):
+            hp[k][...] = v
+        o_rw, o_dn, o_ln = host_array(m, np.int8), host_array(m, np.uint8), host_array((m, 2), np.uint8)
+        rc = a.lib.b2t_step_host(a._h, _hp(hp["idx"], C.c_int32), m, _hp(hp["player"], C.c_uint8), _hp(hp["keys"], C.c_uint8), _hp(hp["klen"], C.c_uint8),
+                                 keys.shape[1], None, 1, 0, _hp(hp["rs"], C.c_uint32), _hp(o_rw, C.c_int8), _hp(o_dn, C.c_uint8), _hp(o_ln, C.c_uint8),
+                                 None, None, None, None, 0, 0)
+        assert rc == 0
+        rw = torch.empty(m, dtype=torch.int8, device=dev); dn = torch.empty(m, dtype=torch.uint8, device=dev); ln = torch.empty((m, 2), dtype=torch.uint8, device=dev)
+        b.step_dev(torch.from_numpy(player).to(dev), torch.from_numpy(keys).to(dev), torch.from_numpy(klen).to(dev), idx=torch.from_numpy(idx).to(dev),
+                   reset_seeds=torch.from_numpy(rs.astype(np.int64)).to(dev).to(torch.int32), reward=rw, done=dn, lines=ln)
+        torch.cuda.synchronize()
+        assert np.array_equal(o_rw, rw.cpu().numpy()) and np.array_equal(o_dn, dn.cpu().numpy()) and np.array_equal(o_ln, ln.cpu().numpy()), t
     assert np.array_equal(a.export_states(), b.export_states())
     a.close(); b.close()
 
