@@ -70,7 +70,7 @@ SYMBOLS = {
     "b2t_observe": (C.c_int, [vp, vp, C.c_int32, C.POINTER(Obs), vp]),
     "b2t_enumerate": (C.c_int, [vp, vp, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_int32, vp]),
     "b2t_expand": (C.c_int, [vp, C.POINTER(ExpandArgs), vp]),
-    "b2t_select": (C.c_int, [vp, vp, vp, C.c_int32, vp, vp]),
+    "b2t_select": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, vp, vp]),
     "b2t_snapshot": (C.c_int, [vp, C.c_int32, vp]),
     "b2t_restore": (C.c_int, [vp, C.c_int32, vp]),
     "b2t_export_state": (C.c_int, [vp, C.c_int32, vp, vp]),
@@ -89,7 +89,7 @@ SYMBOLS = {
     "b2t_observe_host": (C.c_int, [vp, i32p, C.c_int32, u8p, u8p, u8p, i32p]),
     "b2t_enumerate_host": (C.c_int, [vp, i32p, C.c_int32, u8p, i32p, u8p, u8p, C.c_int32, C.c_int32]),
     "b2t_expand_host": (C.c_int, [vp, i32p, C.c_int32, u8p, C.c_int32, C.c_int32, C.c_int32, i32p, i32p, i32p,
-                                  u8p, u8p, C.c_int32, i8p, u8p, u8p, u8p, u8p, u8p]),
+                                  u8p, u8p, C.c_int32, i8p, u8p, u8p, u8p, u8p, u8p, i32p]),
     "b2t_host_alloc": (C.c_int, [C.c_size_t, C.c_int32, C.POINTER(vp)]),
     "b2t_host_free": (C.c_int, [vp]),
     "b2t_debug_streams": (C.c_int, [vp, C.c_uint32, C.c_int32, u8p, u8p]),

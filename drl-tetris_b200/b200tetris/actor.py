@@ -15,7 +15,9 @@ class ActorLoop:
     def __init__(self, engine, score_fn, rows_per_game=40, dtype=None, perspective=True, use_graph=True):
         """score_fn(field[rows,2,H,W], vec[rows,2,19], piece_idx[rows,2], scores[rows]) writes one float32 score per simulated
         placement (rows past offsets[-1] hold stale data; their scores are never read).  rows_per_game sizes the placement
-        buffers (mean list length is ~25 at 22x10; a ply whose placements outgrow the buffers is reported by `overflowed()`)."""
+        buffers (mean list length is ~25 at 22x10, so small vectors should pass rows_per_game=engine.kmax).  A ply whose placements
+        outgrow the buffers stays memory-safe — the rows that did not fit are not simulated and select never reads past the buffers,
+        so the boards at the end of the vector choose among the rows they kept, or placement 0 — and is reported by `overflowed()`."""
         import torch
         self.torch, self.e, self.score_fn = torch, engine, score_fn
         n, H, W = engine.n, engine.H, engine.W
@@ -44,7 +46,7 @@ class ActorLoop:
         e.expand_dev(self.player, self.K, self.offsets, self.cap, field=self.p_field, vec=self.p_vec, piece_idx=self.p_piece,
                      perspective=self.perspective)
         self.score_fn(self.p_field, self.p_vec, self.p_piece, self.scores)
-        e.select_dev(self.scores, self.offsets, self.choice)
+        e.select_dev(self.scores, self.offsets, self.choice, self.cap)
         e.step_dev(self.player, placement=self.choice, auto_reset=True, reward=self.reward, done=self.done, field=self.field,
                    vec=self.vec, piece_idx=self.piece, perspective=self.perspective)
         self.player.bitwise_xor_(1)       # strict alternation of sides (worker.py:96)

@@ -95,6 +95,10 @@ class Engine:
         if idx is None:
             return None, self.n
         idx = np.ascontiguousarray(idx, dtype=np.int32)
+        if idx.ndim != 1:
+            raise ValueError("game ids must be a 1-d list")
+        if len(idx) and (int(idx.min()) < 0 or int(idx.max()) >= self.n):   # the reference's list of envs raises the same way
+            raise IndexError("game id outside [0, %d)" % self.n)
         return idx, len(idx)
 
     # ------------------------------------------------------------------ host-array face (b2t_*_host)
@@ -158,8 +162,9 @@ class Engine:
                                              _hp(keys, C.c_uint8), _hp(klen, C.c_uint8), kmax, lmax))
         return K, keys, klen
 
-    def expand(self, player, idx=None, finalize=True, time_ms=0, capacity=None, lmax=None, want_obs=True):
-        """simulate_all_actions, compact rows.  Returns dict(K, offsets, total, keys, key_len, reward, done, lines, field, vec, piece_idx)."""
+    def expand(self, player, idx=None, finalize=True, time_ms=0, capacity=None, lmax=None, want_obs=True, want_scalars=False):
+        """simulate_all_actions, compact rows.  Returns dict(K, offsets, total, keys, key_len, reward, done, lines, field, vec, piece_idx)
+        and, with want_scalars, scalars i32[capacity,2,8] (the raw State views of every simulated outcome, incl. `dead`)."""
         idx, n = self._idx(idx)
         player = _np(player, np.uint8, n)
         lmax = lmax or self.lmax
@@ -171,11 +176,13 @@ class Engine:
         if want_obs:
             o.update(field=np.zeros((capacity, 2, self.H, self.W), np.uint8), vec=np.zeros((capacity, 2, VEC_LEN), np.uint8),
                      piece_idx=np.zeros((capacity, 2), np.uint8))
+        if want_scalars:
+            o["scalars"] = np.zeros((capacity, 2, 8), np.int32)
         self._ck(self.lib.b2t_expand_host(self._h, _hp(idx, C.c_int32), n, _hp(player, C.c_uint8), int(bool(finalize)), int(time_ms), capacity,
                                           _hp(K, C.c_int32), _hp(offs, C.c_int32), C.byref(total), _hp(o["keys"], C.c_uint8),
                                           _hp(o["key_len"], C.c_uint8), lmax, _hp(o["reward"], C.c_int8), _hp(o["done"], C.c_uint8),
                                           _hp(o["lines"], C.c_uint8), _hp(o.get("field"), C.c_uint8), _hp(o.get("vec"), C.c_uint8),
-                                          _hp(o.get("piece_idx"), C.c_uint8)))
+                                          _hp(o.get("piece_idx"), C.c_uint8), _hp(o.get("scalars"), C.c_int32)))
         o.update(K=K, offsets=offs, total=int(total.value))
         return o
 
@@ -271,9 +278,11 @@ class Engine:
             raise ValueError("field and vec must have the same dtype")
         return kinds.pop() if kinds else _lib.U8
 
-    def select_dev(self, scores, offsets, placement):
-        """argmax of per-placement scores within every board of the last expand_dev -> placement indices for step_dev"""
-        self._ck(self.lib.b2t_select(self._h, self._dp(scores), self._dp(offsets), placement.numel(), self._dp(placement), self._stream()))
+    def select_dev(self, scores, offsets, placement, capacity=None):
+        """argmax of per-placement scores within every board of the last expand_dev -> placement indices for step_dev.  capacity = the
+        capacity given to that expand_dev (default: len(scores)); rows it dropped are never chosen."""
+        cap = scores.numel() if capacity is None else int(capacity)
+        self._ck(self.lib.b2t_select(self._h, self._dp(scores), self._dp(offsets), placement.numel(), cap, self._dp(placement), self._stream()))
 
     def step_dev(self, player, keys=None, key_len=None, idx=None, placement=None, finalize=True, time_ms=0, reset_seeds=None,
                  reward=None, done=None, lines=None, field=None, vec=None, piece_idx=None, scalars=None, perspective=False,

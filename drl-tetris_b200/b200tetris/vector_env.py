@@ -107,11 +107,19 @@ class state:
 
 
 def parse_arg(entry_idx, data, fill_up=None):  # tools/utils.py:10-31
+    """Indices into `data` (the list of envs, or of players) with Python's own indexing rules, which is what the reference gets from
+    `self.envs[i]`: a negative index counts from the end, anything outside raises IndexError."""
+    n = len(data)
+    def norm(i):
+        i = int(i)
+        if not -n <= i < n:
+            raise IndexError("index %d out of range for %d entries" % (i, n))
+        return i + n if i < 0 else i
     if entry_idx is None:
-        return list(range(len(data)))
+        return list(range(n))
     if type(entry_idx) in [list, np.ndarray]:
-        return [int(i) for i in entry_idx]
-    return [int(entry_idx)] if fill_up is None else [int(entry_idx)] * fill_up
+        return [norm(i) for i in entry_idx]
+    return [norm(entry_idx)] if fill_up is None else [norm(entry_idx)] * fill_up
 
 
 class tetris_environment_vector:
@@ -190,10 +198,22 @@ class tetris_environment_vector:
         pl = parse_arg(player, self.player_idxs, fill_up=len(ids))
         n = len(ids)
         assert len(actions) == n and len(pl) == n
-        lmax = max(1, max(len(a) for a in actions))
-        lmax = (lmax + 15) // 16 * 16
         for a in actions:
             assert type(a) in (action, list), "tetris_environment.perform_action(action a,int p) was called with type(action)={}".format(type(a))
+        # key codes outside a byte are no-ops like every other unknown code (PythonHandle.cpp:109-110)
+        actions = [[k if 0 <= k <= 255 else 0 for k in map(int, a)] for a in actions]
+        # A key list longer than the engine's sequence capacity (press_key-style callers may send anything) is applied in pieces, as
+        # the per-env facade does (tetris_env._step): its leading keys go down in make_action-only launches, the tail with the finish.
+        cap = self.engine.lmax
+        long_ = [j for j, a in enumerate(actions) if len(a) > cap]
+        while long_:
+            head = np.array([actions[j][:cap] for j in long_], np.uint8)
+            self.engine.step([pl[j] for j in long_], head, np.full(len(long_), cap, np.uint8), [ids[j] for j in long_], finalize=False)
+            for j in long_:
+                actions[j] = actions[j][cap:]
+            long_ = [j for j in long_ if len(actions[j]) > cap]
+        lmax = max(1, max(len(a) for a in actions))
+        lmax = (lmax + 15) // 16 * 16
         klen = np.fromiter(map(len, actions), np.int64, n)
         keys = np.zeros((n, lmax), np.uint8)
         keys[np.arange(lmax)[None, :] < klen[:, None]] = np.fromiter((k for a in actions for k in a), np.uint8, int(klen.sum()))
@@ -232,11 +252,12 @@ class tetris_environment_vector:
     def simulate_all_actions(self, env=None, player=None, finalize=True):  # :93-97 ; tetris_environment :127-129,87-100
         ids = parse_arg(env, self.envs)
         pl = parse_arg(player, self.player_idxs, fill_up=len(ids))
-        o = self.engine.expand(pl, ids, finalize=finalize)
+        o = self.engine.expand(pl, ids, finalize=finalize, want_scalars=True)
+        dead = o["scalars"][:, :, 7]      # states[p].dead of every simulated outcome (data_types/state.py:9-17 is_dead)
         out = []
         for j in range(len(ids)):
             a, b = o["offsets"][j], o["offsets"][j + 1]
-            out.append([state(o["field"][r], o["vec"][r], o["piece_idx"][r], [0, 0]) for r in range(a, b)])
+            out.append([state(o["field"][r], o["vec"][r], o["piece_idx"][r], dead[r]) for r in range(a, b)])
         return out
 
     def simulate_actions(self, actions, env=None, player=None, finalize=True):  # :73-77 ; tetris_environment.simulate_actions :87-100
@@ -263,6 +284,12 @@ class tetris_environment_vector:
         other.engine.import_states(self.engine.export_states())
         other.done[:] = self.done
         other._dead[:] = self._dead
+        # the bookkeeping of the rounds so far travels too: the copy continues the original's seed sequence and reward totals
+        other._seed0 = self._seed0
+        other._episode[:] = self._episode
+        other.rounds_played[:] = self.rounds_played
+        other.round_reward = [[reward(r.extrinsic) for r in rr] for rr in self.round_reward]
+        other.tot_reward = [[reward(r.extrinsic) for r in rr] for rr in self.tot_reward]
         return other
 
     def get_info(self, env=None):  # tetris_environment.get_info :151-160

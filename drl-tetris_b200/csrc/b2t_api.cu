@@ -92,6 +92,24 @@ static int fail(b2t_handle* h, int code, const char* fmt, const char* a = "", lo
 constexpr int PIPE_MIN_ROWS = 1 << 16;   // b2t_step_host: batches at least this large are sliced over two streams
 constexpr int PIPE_SLICES = 2;       // measured on the B200 box: H2D (25-38 GB/s pinned) bounds the call; 2 slices 0.68 ms, 1: 0.74, 8: 0.92 (profiles/e2e_probe.py)
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+// every id of a caller's HOST game list must name a game of the handle (the kernels ignore rows whose id does not, but a host call
+// answers with an error the way the reference's list indexing raises IndexError)
+static bool ids_in_range(const int32_t* h_idx, int32_t n, int32_t n_games) {
+    if (!h_idx) return true;
+    uint32_t worst = 0;
+    for (int32_t i = 0; i < n; i++) { const uint32_t v = (uint32_t)h_idx[i]; worst = v > worst ? v : worst; }
+    return n <= 0 || worst < (uint32_t)n_games;
+}
+#define CK_IDS(name)                                                                                                   \
+    do {                                                                                                               \
+        if (!ids_in_range(h_idx, n, h->cfg.n_games)) return fail(h, B2T_ERR_ARG, name ": game id outside [0, n_games)%s"); \
+    } while (0)
+// Streams of a pipelined host call are drained on every way out, so no asynchronous copy still touches the caller's buffers or the
+// arenas after the call has returned (an error return included)
+struct StreamDrain {
+    cudaStream_t a, b;
+    ~StreamDrain() { if (a) cudaStreamSynchronize(a); if (b) cudaStreamSynchronize(b); }
+};
 
 extern "C" {
 
@@ -284,7 +302,7 @@ int b2t_enumerate(b2t_handle* h, const int32_t* d_idx, int32_t n, const uint8_t*
     e.bar_null = h->cfg.bar_null_moves ? 1 : 0; e.plc = h->plc; e.kcache = h->kcache; e.K = d_K; e.stats = h->stats; e.tabs = h->tabs;
     CK(h->ops->launch_enum(e, (cudaStream_t)stream));
     h->enumerated = true;
-    if (d_keys || d_key_len) CK(h->ops->launch_unpack(h->plc, h->kcache, d_idx, n, kmax, lmax, d_keys, d_key_len, (cudaStream_t)stream));
+    if (d_keys || d_key_len) CK(h->ops->launch_unpack(h->plc, h->kcache, d_idx, h->cfg.n_games, n, kmax, lmax, d_keys, d_key_len, (cudaStream_t)stream));
     return B2T_OK;
 }
 
@@ -326,10 +344,10 @@ int b2t_expand(b2t_handle* h, const b2t_expand_args* a, void* stream) {
     return B2T_OK;
 }
 
-int b2t_select(b2t_handle* h, const float* d_scores, const int32_t* d_offsets, int32_t n, int32_t* d_placement, void* stream) {
-    if (!h || !d_scores || !d_offsets || !d_placement || n < 0) return fail(h, B2T_ERR_ARG, "b2t_select: NULL argument or n < 0%s");
+int b2t_select(b2t_handle* h, const float* d_scores, const int32_t* d_offsets, int32_t n, int32_t capacity, int32_t* d_placement, void* stream) {
+    if (!h || !d_scores || !d_offsets || !d_placement || n < 0 || capacity < 0) return fail(h, B2T_ERR_ARG, "b2t_select: NULL argument, n < 0 or capacity < 0%s");
     CK(cudaSetDevice(h->cfg.device));
-    if (n) select_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_scores, d_offsets, n, d_placement);
+    if (n) select_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_scores, d_offsets, n, capacity, d_placement);
     CK(cudaGetLastError());
     return B2T_OK;
 }
@@ -479,11 +497,20 @@ static void* dev_out(const Arena& a, const Out& o) { return o.dst ? a.d + o.off 
 // Pinned (cudaMallocHost / cudaHostRegister'ed, e.g. torch pin_memory) caller buffers are copied straight to / from the
 // device arena; pageable ones go through the handle's pinned staging (one extra host memcpy).
 constexpr size_t DIRECT_COPY_MIN = 1 << 16;   // smaller arrays go through the handle's pinned staging without asking the driver
-static bool is_pinned(const void* p) {
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return at.type == cudaMemoryTypeHost;
+// device address of a pinned / registered host range, or NULL: the first AND the last byte must resolve to host memory of one
+// mapping (a buffer that is only partly registered does not pass)
+static void* mapped_range(const void* p, size_t bytes) {
+    if (!p) return nullptr;
+    cudaPointerAttributes a0, a1;
+    if (cudaPointerGetAttributes(&a0, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a0.type != cudaMemoryTypeHost || !a0.devicePointer) return nullptr;
+    if (bytes > 1) {
+        if (cudaPointerGetAttributes(&a1, (const unsigned char*)p + bytes - 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (a1.type != cudaMemoryTypeHost || (unsigned char*)a1.devicePointer != (unsigned char*)a0.devicePointer + bytes - 1) return nullptr;
+    }
+    return a0.devicePointer;
 }
+static bool is_pinned(const void* p, size_t bytes) { return mapped_range(p, bytes) != nullptr; }
 static int stage_in(b2t_handle* h, std::vector<In*> ins, cudaStream_t s) {
     size_t total = 0;
     for (auto i : ins) if (i->src) total += (i->bytes + 255) & ~(size_t)255;
@@ -492,7 +519,7 @@ static int stage_in(b2t_handle* h, std::vector<In*> ins, cudaStream_t s) {
         if (!i->src || !i->bytes) { if (i->src) i->off = h->in.take(1); continue; }
         i->off = h->in.take(i->bytes);
         const void* from = i->src;
-        if (i->bytes < DIRECT_COPY_MIN || !is_pinned(from)) { memcpy(h->in.h + i->off, i->src, i->bytes); from = h->in.h + i->off; }
+        if (i->bytes < DIRECT_COPY_MIN || !is_pinned(from, i->bytes)) { memcpy(h->in.h + i->off, i->src, i->bytes); from = h->in.h + i->off; }
         CK(cudaMemcpyAsync(h->in.d + i->off, from, i->bytes, cudaMemcpyHostToDevice, s));
     }
     return B2T_OK;
@@ -508,7 +535,7 @@ static int fetch_out(b2t_handle* h, std::vector<Out*> outs, cudaStream_t s) {
     std::vector<Out*> staged;
     for (auto o : outs) {
         if (!o->dst || !o->bytes) continue;
-        if (o->bytes >= DIRECT_COPY_MIN && is_pinned(o->dst)) CK(cudaMemcpyAsync(o->dst, h->out.d + o->off, o->bytes, cudaMemcpyDeviceToHost, s));
+        if (o->bytes >= DIRECT_COPY_MIN && is_pinned(o->dst, o->bytes)) CK(cudaMemcpyAsync(o->dst, h->out.d + o->off, o->bytes, cudaMemcpyDeviceToHost, s));
         else { CK(cudaMemcpyAsync(h->out.h + o->off, h->out.d + o->off, o->bytes, cudaMemcpyDeviceToHost, s)); staged.push_back(o); }
     }
     CK(cudaStreamSynchronize(s));
@@ -519,6 +546,7 @@ static int fetch_out(b2t_handle* h, std::vector<Out*> outs, cudaStream_t s) {
 int b2t_export_states(b2t_handle* h, const int32_t* h_idx, int32_t n, void* h_buf) {
     if (!h || !h_buf || n < 0 || n > h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_export_states: bad argument%s");
     if (!n) return B2T_OK;
+    CK_IDS("b2t_export_states");
     CK(cudaSetDevice(h->cfg.device));
     const size_t bytes = (size_t)n * h->ops->NV * 16;
     In idx; idx.src = h_idx; idx.bytes = (size_t)n * 4;
@@ -526,18 +554,19 @@ int b2t_export_states(b2t_handle* h, const int32_t* h_idx, int32_t n, void* h_bu
     Out buf; buf.dst = h_buf; buf.bytes = bytes;
     if (int r = plan_out(h, {&buf})) return r;
     const long long t = (long long)n * h->ops->NV;
-    gather_games_kernel<<<(unsigned)((t + 255) / 256), 256>>>(h->state, (const int32_t*)dev_in(h->in, idx), n, h->ops->NV, (uint4*)dev_out(h->out, buf));
+    gather_games_kernel<<<(unsigned)((t + 255) / 256), 256>>>(h->state, h->cfg.n_games, (const int32_t*)dev_in(h->in, idx), n, h->ops->NV, (uint4*)dev_out(h->out, buf));
     CK(cudaGetLastError());
     return fetch_out(h, {&buf}, 0);
 }
 int b2t_import_states(b2t_handle* h, const int32_t* h_idx, int32_t n, const void* h_buf) {
     if (!h || !h_buf || n < 0 || n > h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_import_states: bad argument%s");
     if (!n) return B2T_OK;
+    CK_IDS("b2t_import_states");
     CK(cudaSetDevice(h->cfg.device));
     In idx, buf; idx.src = h_idx; idx.bytes = (size_t)n * 4; buf.src = h_buf; buf.bytes = (size_t)n * h->ops->NV * 16;
     if (int r = stage_in(h, {&idx, &buf}, 0)) return r;
     const long long t = (long long)n * h->ops->NV;
-    scatter_games_kernel<<<(unsigned)((t + 255) / 256), 256>>>(h->state, (const int32_t*)dev_in(h->in, idx), n, h->ops->NV, (const uint4*)dev_in(h->in, buf));
+    scatter_games_kernel<<<(unsigned)((t + 255) / 256), 256>>>(h->state, h->cfg.n_games, (const int32_t*)dev_in(h->in, idx), n, h->ops->NV, (const uint4*)dev_in(h->in, buf));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(0));
     return B2T_OK;
@@ -546,6 +575,7 @@ int b2t_import_states(b2t_handle* h, const int32_t* h_idx, int32_t n, const void
 int b2t_reset_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint32_t* h_seeds) {
     if (!h) return B2T_ERR_ARG;
     if (n < 0 || n > h->cfg.n_games || !h_seeds) return fail(h, B2T_ERR_ARG, "b2t_reset_host: bad n or NULL seeds%s");
+    CK_IDS("b2t_reset_host");
     CK(cudaSetDevice(h->cfg.device));
     In idx, seeds;
     idx.src = h_idx; idx.bytes = (size_t)n * 4; seeds.src = h_seeds; seeds.bytes = (size_t)n * 4;
@@ -561,6 +591,7 @@ int b2t_step_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint8_t*
                   int32_t* h_scalars, int32_t key_format, int32_t auto_reset) {
     if (!h) return B2T_ERR_ARG;
     if (n < 0 || n > h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_step_host: bad n%s");
+    CK_IDS("b2t_step_host");
     CK(cudaSetDevice(h->cfg.device));
     const size_t N = (size_t)n, HW = (size_t)h->ops->H * h->ops->W;
     In idx, pl, keys, klen, plc, rs;
@@ -577,20 +608,23 @@ int b2t_step_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint8_t*
         // lines straight through the caller's pinned pages (they are device-addressable under unified addressing), so the
         // PCIe traffic overlaps the compute inside ONE launch instead of being copies before and after it.
         static const bool zero_copy = !(getenv("B2T_ZERO_COPY") && atoi(getenv("B2T_ZERO_COPY")) == 0);
-        auto mapped = [](const void* p) -> void* {
-            if (!p) return nullptr;
-            cudaPointerAttributes at;
-            if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-            return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+        // the kernel loads ids / placements / seeds as 32-bit words and stores the line counts as 16-bit pairs: a host pointer that
+        // is not naturally aligned for that (a sliced array) takes the staged path instead of faulting on the device
+        auto mapped = [](const void* p, size_t bytes, size_t align) -> void* {
+            if (!p || (reinterpret_cast<uintptr_t>(p) & (align - 1))) return nullptr;
+            void* d = mapped_range(p, bytes);
+            return (d && !(reinterpret_cast<uintptr_t>(d) & (align - 1))) ? d : nullptr;
         };
         if (zero_copy && n >= PIPE_MIN_ROWS && !h_field && !h_vec && !h_piece_idx && !h_scalars) {
             const void* ins_h[6] = {h_idx, h_player, h_keys, h_key_len, h_placement, h_reset_seeds};
+            const size_t ins_b[6] = {idx.bytes, pl.bytes, keys.bytes, klen.bytes, plc.bytes, rs.bytes}, ins_a[6] = {4, 1, 1, 1, 4, 4};
             void* outs_h[3] = {h_reward, h_done, h_lines};
+            const size_t outs_b[3] = {rew.bytes, done.bytes, lines.bytes}, outs_a[3] = {1, 1, 2};
             void* ins_d[6];
             void* outs_d[3];
             bool ok = true;
-            for (int k = 0; k < 6; k++) { ins_d[k] = mapped(ins_h[k]); ok = ok && (!ins_h[k] || ins_d[k]); }
-            for (int k = 0; k < 3; k++) { outs_d[k] = mapped(outs_h[k]); ok = ok && (!outs_h[k] || outs_d[k]); }
+            for (int k = 0; k < 6; k++) { ins_d[k] = mapped(ins_h[k], ins_b[k], ins_a[k]); ok = ok && (!ins_h[k] || ins_d[k]); }
+            for (int k = 0; k < 3; k++) { outs_d[k] = mapped(outs_h[k], outs_b[k], outs_a[k]); ok = ok && (!outs_h[k] || outs_d[k]); }
             if (ok) {
                 b2t_step_args a;
                 memset(&a, 0, sizeof a);
@@ -619,9 +653,10 @@ int b2t_step_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint8_t*
         if (int r = plan_out(h, outs)) return r;
         for (auto& st : h->pipe) if (!st) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         CK(cudaStreamSynchronize(0));               // earlier work of this handle went to the default stream
+        StreamDrain drain{h->pipe[0], h->pipe[1]};
         bool pinned_in[6], pinned_out[7];
-        for (int k = 0; k < 6; k++) pinned_in[k] = ins[k]->src && is_pinned(ins[k]->src);
-        for (int k = 0; k < 7; k++) pinned_out[k] = outs[k]->dst && is_pinned(outs[k]->dst);
+        for (int k = 0; k < 6; k++) pinned_in[k] = ins[k]->src && is_pinned(ins[k]->src, ins[k]->bytes);
+        for (int k = 0; k < 7; k++) pinned_out[k] = outs[k]->dst && is_pinned(outs[k]->dst, outs[k]->bytes);
         static const int slices_env = getenv("B2T_PIPE_SLICES") ? atoi(getenv("B2T_PIPE_SLICES")) : 0;   // tuning knob
         const int slices = slices_env > 0 ? slices_env : PIPE_SLICES;
         const int per = (((n + slices - 1) / slices) + 1023) & ~1023;      // slice starts stay 16-byte aligned in every array
@@ -683,6 +718,7 @@ int b2t_step_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint8_t*
 int b2t_observe_host(b2t_handle* h, const int32_t* h_idx, int32_t n, uint8_t* h_field, uint8_t* h_vec, uint8_t* h_piece_idx, int32_t* h_scalars) {
     if (!h) return B2T_ERR_ARG;
     if (n < 0 || n > h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_observe_host: bad n%s");
+    CK_IDS("b2t_observe_host");
     CK(cudaSetDevice(h->cfg.device));
     const size_t N = (size_t)n, HW = (size_t)h->ops->H * h->ops->W;
     In idx; idx.src = h_idx; idx.bytes = N * 4;
@@ -703,6 +739,7 @@ int b2t_enumerate_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uin
                        uint8_t* h_key_len, int32_t kmax, int32_t lmax) {
     if (!h) return B2T_ERR_ARG;
     if (n < 0 || n > h->cfg.n_games || !h_player) return fail(h, B2T_ERR_ARG, "b2t_enumerate_host: bad n or NULL player%s");
+    CK_IDS("b2t_enumerate_host");
     CK(cudaSetDevice(h->cfg.device));
     const size_t N = (size_t)n;
     In idx, pl; idx.src = h_idx; idx.bytes = N * 4; pl.src = h_player; pl.bytes = N;
@@ -717,14 +754,16 @@ int b2t_enumerate_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uin
 
 int b2t_expand_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint8_t* h_player, int32_t finalize, int32_t time_ms,
                     int32_t capacity, int32_t* h_K, int32_t* h_offsets, int32_t* h_total, uint8_t* h_keys, uint8_t* h_key_len, int32_t lmax,
-                    int8_t* h_reward, uint8_t* h_done, uint8_t* h_lines, uint8_t* h_field, uint8_t* h_vec, uint8_t* h_piece_idx) {
+                    int8_t* h_reward, uint8_t* h_done, uint8_t* h_lines, uint8_t* h_field, uint8_t* h_vec, uint8_t* h_piece_idx,
+                    int32_t* h_scalars) {
     if (!h) return B2T_ERR_ARG;
     if (n < 1 || n > h->cfg.n_games || !h_player || capacity < 0) return fail(h, B2T_ERR_ARG, "b2t_expand_host: bad n/capacity or NULL player%s");
+    CK_IDS("b2t_expand_host");
     CK(cudaSetDevice(h->cfg.device));
     const size_t N = (size_t)n, C = (size_t)capacity, HW = (size_t)h->ops->H * h->ops->W;
     In idx, pl; idx.src = h_idx; idx.bytes = N * 4; pl.src = h_player; pl.bytes = N;
     if (int r = stage_in(h, {&idx, &pl}, 0)) return r;
-    Out K, offs, keys, klen, rew, done, lines, field, vec, pidx;
+    Out K, offs, keys, klen, rew, done, lines, field, vec, pidx, scal;
     std::vector<int32_t> k_tmp, o_tmp;
     if (!h_K) { k_tmp.resize(N); h_K = k_tmp.data(); }
     if (!h_offsets) { o_tmp.resize(N + 1); h_offsets = o_tmp.data(); }
@@ -732,7 +771,8 @@ int b2t_expand_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint8_
     keys.dst = h_keys; keys.bytes = C * (size_t)(lmax > 0 ? lmax : 0); klen.dst = h_key_len; klen.bytes = C;
     rew.dst = h_reward; rew.bytes = C; done.dst = h_done; done.bytes = C; lines.dst = h_lines; lines.bytes = 2 * C;
     field.dst = h_field; field.bytes = 2 * HW * C; vec.dst = h_vec; vec.bytes = 2 * B2T_VEC_LEN * C; pidx.dst = h_piece_idx; pidx.bytes = 2 * C;
-    if (int r = plan_out(h, {&K, &offs, &keys, &klen, &rew, &done, &lines, &field, &vec, &pidx})) return r;
+    scal.dst = h_scalars; scal.bytes = 64 * C;
+    if (int r = plan_out(h, {&K, &offs, &keys, &klen, &rew, &done, &lines, &field, &vec, &pidx, &scal})) return r;
     b2t_expand_args a;
     memset(&a, 0, sizeof a);
     a.d_game_idx = (const int32_t*)dev_in(h->in, idx); a.n = n; a.d_player = (const uint8_t*)dev_in(h->in, pl);
@@ -741,8 +781,9 @@ int b2t_expand_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint8_
     a.d_keys = (uint8_t*)dev_out(h->out, keys); a.d_key_len = (uint8_t*)dev_out(h->out, klen); a.lmax = lmax;
     a.d_reward = (int8_t*)dev_out(h->out, rew); a.d_done = (uint8_t*)dev_out(h->out, done); a.d_lines = (uint8_t*)dev_out(h->out, lines);
     a.obs.d_field = (uint8_t*)dev_out(h->out, field); a.obs.d_vec = (uint8_t*)dev_out(h->out, vec); a.obs.d_piece_idx = (uint8_t*)dev_out(h->out, pidx);
+    a.obs.d_scalars = (int32_t*)dev_out(h->out, scal);
     if (int r = b2t_expand(h, &a, nullptr)) return r;
-    if (int r = fetch_out(h, {&K, &offs, &keys, &klen, &rew, &done, &lines, &field, &vec, &pidx}, 0)) return r;
+    if (int r = fetch_out(h, {&K, &offs, &keys, &klen, &rew, &done, &lines, &field, &vec, &pidx, &scal}, 0)) return r;
     if (h_total) *h_total = h_offsets[n];
     return B2T_OK;
 }

@@ -358,19 +358,24 @@ __global__ void __launch_bounds__(TPB, MODE == GM_EXPAND ? B2T_GAME_MINB + 1 : B
         total_rows = p.offsets[p.n];
         if (total_rows > p.capacity) total_rows = p.capacity;
     }
-    const bool active = row < total_rows;
     // per-thread stat contributions
     int st_steps = 0, st_done = 0, st_w0 = 0, st_w1 = 0, st_both = 0, st_lines = 0, st_gq = 0, st_rng = 0;
     int obs_player = 0;
-
+    int gi = 0, player = 0, sel = 0, nkeys = 0;
+    bool active = row < total_rows;
     if (active) {
-        // ---- every global load that does not depend on the state is issued before the state itself
-        int gi, player = 0, sel = 0, nkeys = 0;
         if (expand) {
             const int4 m = p.row_meta[row];
             i = m.x; gi = m.y; k = m.z; player = m.w; sel = k;
-        } else {
-            gi = p.idx ? p.idx[i] : i + p.game0;
+        } else gi = p.idx ? p.idx[i] : i + p.game0;
+        // a game id outside the handle (the caller's list is never trusted with the state array, the placement cache or kcache):
+        // the row is inert — nothing is read or written for it and its observation rows come out as zeros
+        active = (unsigned)gi < (unsigned)p.n_games;
+    }
+
+    if (active) {
+        // ---- every global load that does not depend on the state is issued before the state itself
+        if (!expand) {
             if (stepping) {
                 player = p.player[i] ? 1 : 0;
                 if (p.placement) sel = p.placement[i]; else nkeys = (MODE != GM_GENERIC || p.key_len) ? (int)p.key_len[i] : -1;
@@ -702,10 +707,16 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
     b.stream = nullptr;
     if (has) board_init_walls<G, ENB>(b);
     __syncthreads();
-    const bool active = has && i < p.n;
+    bool active = has && i < p.n;
     int gi = 0, kind = 7, cur_rot = 0;
     if (active) {
         gi = p.idx ? p.idx[i] : i;
+        if ((unsigned)gi >= (unsigned)p.n_games) {   // id outside the handle: an empty list, nothing touched
+            active = false; gi = 0;
+            if (p.K) p.K[i] = 0;
+        }
+    }
+    if (active) {
         const int pl = p.player[i] ? 1 : 0;
         const uint32_t* words = reinterpret_cast<const uint32_t*>(p.state);
         auto word = [&](int wi) { return words[state_index<G>(gi, wi >> 2) * 4 + (wi & 3)]; };
@@ -894,14 +905,15 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
 
 // packed cache -> the u8 [n,kmax,lmax] / [n,kmax] arrays of the reference-shaped API
 template <class G>
-__global__ void unpack_keys_kernel(const uint32_t* plc, const int32_t* kcache, const int32_t* idx, int n, int kmax, int lmax,
+__global__ void unpack_keys_kernel(const uint32_t* plc, const int32_t* kcache, const int32_t* idx, int n_games, int n, int kmax, int lmax,
                                    uint8_t* keys, uint8_t* key_len) {
     constexpr int KW = G::KEYW;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)n * kmax) return;
     const int i = (int)(t / kmax), k = (int)(t % kmax);
     const int gi = idx ? idx[i] : i;
-    const int K = kcache[gi];
+    const bool in_range = (unsigned)gi < (unsigned)n_games;
+    const int K = in_range ? kcache[gi] : 0;
     uint32_t w[KW];
     const bool valid = k < K && k < G::KMAX;
     for (int j = 0; j < KW; j++) w[j] = valid ? plc[((size_t)gi * G::KMAX + k) * KW + j] : 0u;
@@ -962,10 +974,14 @@ __global__ void __launch_bounds__(SCAN_TPB) scan_sums(int32_t* sums, int tiles) 
 }
 // phase 3: offsets
 // segmented argmax of the caller's per-placement scores: first maximum wins, like numpy.argmax
-__global__ void __launch_bounds__(256) select_kernel(const float* scores, const int32_t* offsets, int n, int32_t* placement) {
+// rows at or past `capacity` were dropped by the expand that produced the offsets (never simulated, no score): they cannot be chosen; a
+// board with no surviving row takes placement 0
+__global__ void __launch_bounds__(256) select_kernel(const float* scores, const int32_t* offsets, int n, int capacity, int32_t* placement) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int a = offsets[i], b = offsets[i + 1];
+    int a = offsets[i], b = offsets[i + 1];
+    if (b > capacity) b = capacity;
+    if (a > b) a = b;
     int best = 0;
     float bv = (b > a) ? scores[a] : 0.f;
     for (int r = a + 1; r < b; r++) {
@@ -1074,17 +1090,17 @@ __global__ void copy_tiles_kernel(uint32_t* dst_tiles, int dst, const uint32_t* 
     if (w < nw) dst_tiles[((size_t)(dst >> 5) * nw + w) * 32 + (dst & 31)] = src_tiles ? src_tiles[((size_t)(src >> 5) * nw + w) * 32 + (src & 31)] : 0u;
 }
 // n games' vectors <-> one contiguous buffer [n][nv] (batched export / import: get_state of a whole vector of envs)
-__global__ void gather_games_kernel(const uint4* state, const int32_t* idx, int n, int nv, uint4* out) {
+__global__ void gather_games_kernel(const uint4* state, int n_games, const int32_t* idx, int n, int nv, uint4* out) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)n * nv) return;
     const int i = (int)(t / nv), v = (int)(t % nv), game = idx ? idx[i] : i;
-    out[t] = state[((size_t)(game >> 5) * nv + v) * 32 + (game & 31)];
+    out[t] = (unsigned)game < (unsigned)n_games ? state[((size_t)(game >> 5) * nv + v) * 32 + (game & 31)] : make_uint4(0u, 0u, 0u, 0u);
 }
-__global__ void scatter_games_kernel(uint4* state, const int32_t* idx, int n, int nv, const uint4* in) {
+__global__ void scatter_games_kernel(uint4* state, int n_games, const int32_t* idx, int n, int nv, const uint4* in) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)n * nv) return;
     const int i = (int)(t / nv), v = (int)(t % nv), game = idx ? idx[i] : i;
-    state[((size_t)(game >> 5) * nv + v) * 32 + (game & 31)] = in[t];
+    if ((unsigned)game < (unsigned)n_games) state[((size_t)(game >> 5) * nv + v) * 32 + (game & 31)] = in[t];
 }
 // PythonHandle.copy()/set() of one game, possibly between two handles of the same field size
 __global__ void copy_game_kernel(uint4* dst_state, int dst, const uint4* src_state, int src, int nv) {
@@ -1100,7 +1116,7 @@ struct GeomOps {
     cudaError_t (*prepare)();
     cudaError_t (*launch_game)(const KParams&, int rows, cudaStream_t);
     cudaError_t (*launch_enum)(const EParams&, cudaStream_t);
-    cudaError_t (*launch_unpack)(const uint32_t*, const int32_t*, const int32_t*, int, int, int, uint8_t*, uint8_t*, cudaStream_t);
+    cudaError_t (*launch_unpack)(const uint32_t*, const int32_t*, const int32_t*, int, int, int, int, uint8_t*, uint8_t*, cudaStream_t);
     cudaError_t (*launch_init)(uint4*, int, cudaStream_t);
     void (*decode)(const uint32_t* words, b2t_game_raw* out, uint8_t* field, const uint32_t* planes);          // host codec, b2t_raw.cuh
     void (*encode)(uint32_t* words, const b2t_game_raw* in, const uint8_t* field, uint32_t* planes);
@@ -1135,11 +1151,11 @@ template <class G> struct Launch {
         enumerate_kernel<G><<<(p.n + ENB - 1) / ENB, ETPB, EnumCfg<G>::SMEM, s>>>(p);
         return cudaGetLastError();
     }
-    static cudaError_t unpack(const uint32_t* plc, const int32_t* kc, const int32_t* idx, int n, int kmax, int lmax, uint8_t* keys,
+    static cudaError_t unpack(const uint32_t* plc, const int32_t* kc, const int32_t* idx, int n_games, int n, int kmax, int lmax, uint8_t* keys,
                               uint8_t* key_len, cudaStream_t s) {
         const long long t = (long long)n * kmax;
         if (t <= 0) return cudaSuccess;
-        unpack_keys_kernel<G><<<(unsigned)((t + 255) / 256), 256, 0, s>>>(plc, kc, idx, n, kmax, lmax, keys, key_len);
+        unpack_keys_kernel<G><<<(unsigned)((t + 255) / 256), 256, 0, s>>>(plc, kc, idx, n_games, n, kmax, lmax, keys, key_len);
         return cudaGetLastError();
     }
     static cudaError_t init(uint4* state, int n, cudaStream_t s) {

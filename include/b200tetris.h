@@ -13,7 +13,11 @@
  *     *_host calls run on the legacy default stream (plus two internal streams for large batches) and synchronise before
  *     returning; a caller that also drives the handle from non-blocking streams of its own orders the two itself.
  *   - game_idx == NULL means "games 0..n-1"; otherwise n distinct game ids (duplicates in one call are undefined,
- *     like stepping one PythonHandle from two threads).
+ *     like stepping one PythonHandle from two threads).  Ids must lie in [0, n_games): a *_host call answers B2T_ERR_ARG for a
+ *     list that holds any other id (the reference raises IndexError); a device-pointer call cannot look at the list, so its
+ *     kernels treat such a row as inert — no game is read or written, its outputs are zeros / untouched, its K is 0.
+ *   - h_* arrays may have any alignment; the zero-copy path of b2t_step_host is only taken when every array is naturally
+ *     aligned for its element type and pinned over its whole length.
  *   - a handle is not thread-safe (neither is the reference); handles on different devices are independent.
  *   - there is NO CPU fallback: without a CUDA device b2t_create fails with B2T_ERR_CUDA.
  */
@@ -27,7 +31,7 @@
 extern "C" {
 #endif
 
-#define B2T_ABI_VERSION 2
+#define B2T_ABI_VERSION 3
 #define B2T_VEC_LEN 19  /* x,y,incoming_lines,combo_time,combo_count,nextpiece[7],piece[7]  (state_processors.py:33-41) */
 #define B2T_SNAPSHOT_SLOTS 4
 
@@ -171,8 +175,11 @@ int b2t_expand(b2t_handle *h, const b2t_expand_args *a, void *stream);
 /* The select step of the actor loop (sventon_agent: evaluate every placement, act on the best): for every board of the last
  * b2t_expand, the placement with the highest score, first one on ties like numpy.argmax.  d_scores [total] float32 in the row
  * order of b2t_expand; d_placement [n] is what b2t_step takes as d_placement.  Asynchronous, no host round trip: enumerate ->
- * expand -> (caller's network) -> select -> step can be captured in one CUDA graph. */
-int b2t_select(b2t_handle *h, const float *d_scores, const int32_t *d_offsets, int32_t n, int32_t *d_placement, void *stream);
+ * expand -> (caller's network) -> select -> step can be captured in one CUDA graph.  `capacity` is the capacity that b2t_expand
+ * was given (= rows of d_scores): rows it dropped (offsets beyond capacity) have no score and are never chosen; a board left
+ * without any row takes placement 0. */
+int b2t_select(b2t_handle *h, const float *d_scores, const int32_t *d_offsets, int32_t n, int32_t capacity, int32_t *d_placement,
+               void *stream);
 
 /* PythonHandle.copy() / PythonHandle.set() for the whole vector (PythonHandle.cpp:36-42; tetris_environment.py:165-176) */
 int b2t_snapshot(b2t_handle *h, int32_t slot, void *stream);
@@ -259,7 +266,7 @@ int b2t_enumerate_host(b2t_handle *h, const int32_t *h_game_idx, int32_t n, cons
 int b2t_expand_host(b2t_handle *h, const int32_t *h_game_idx, int32_t n, const uint8_t *h_player, int32_t finalize,
                     int32_t time_ms, int32_t capacity, int32_t *h_K, int32_t *h_offsets, int32_t *h_total,
                     uint8_t *h_keys, uint8_t *h_key_len, int32_t lmax, int8_t *h_reward, uint8_t *h_done, uint8_t *h_lines,
-                    uint8_t *h_field, uint8_t *h_vec, uint8_t *h_piece_idx);
+                    uint8_t *h_field, uint8_t *h_vec, uint8_t *h_piece_idx, int32_t *h_scalars /* optional [capacity,2,8] */);
 
 /* Pinned host memory for the *_host entry points (buffers allocated here, or pinned by the caller in any other way, are copied
  * without the staging pass).  write_combined != 0 asks for write-combined pages: slow for the host to READ, but the device's

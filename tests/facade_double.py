@@ -43,7 +43,7 @@ class HostSimEngine:
         o = self.v.observe(idx)
         return o + (self.v.scal(idx),) if want_scalars else o
 
-    def expand(self, player, idx=None, finalize=True, time_ms=0, capacity=None, lmax=None, want_obs=True):
+    def expand(self, player, idx=None, finalize=True, time_ms=0, capacity=None, lmax=None, want_obs=True, want_scalars=False):
         """compact rows like b2t_expand_host, from the host sim's padded result"""
         kmax, lmax = self.kmax, lmax or self.lmax
         o = self.v.expand(player, idx, self.bar_null, finalize, time_ms if time_ms > 0 else self.default_ms, kmax, lmax)
@@ -53,6 +53,10 @@ class HostSimEngine:
         out = {"K": K, "offsets": offs, "total": int(offs[-1])}
         for name in ("keys", "key_len", "reward", "done", "lines", "field", "vec", "piece_idx"):
             out[name] = np.concatenate([o[name][i, :K[i]] for i in range(len(K))]) if len(K) else o[name][:0, 0]
+        if want_scalars:   # only the `dead` column (7) is filled: it is the one the vector env reads from simulated outcomes
+            dead = np.concatenate([o["dead"][i, :K[i]] for i in range(len(K))]) if len(K) else o["dead"][:0, 0]
+            out["scalars"] = np.zeros((len(dead), 2, 8), np.int32)
+            out["scalars"][:, :, 7] = dead
         return out
 
     def export_states(self, idx=None):

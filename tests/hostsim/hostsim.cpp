@@ -29,7 +29,7 @@ struct HSBase {
                           uint8_t* keys, uint8_t* key_len) = 0;
     virtual int expand(const int32_t* idx, int n, const uint8_t* player, int bar_null, int finalize, int time_ms, int kmax, int lmax,
                        int32_t* K, uint8_t* keys, uint8_t* key_len, uint8_t* field, uint8_t* vec, uint8_t* pidx, int8_t* reward,
-                       uint8_t* done, uint8_t* lines) = 0;
+                       uint8_t* done, uint8_t* lines, uint8_t* dead) = 0;
     virtual int flags(int game) = 0;
     virtual void get_game(int game, b2t_game_raw* out, uint8_t* field) = 0;
     virtual void set_game(int game, const b2t_game_raw* in, const uint8_t* field) = 0;
@@ -225,7 +225,7 @@ template <int H, int W> struct HS : HSBase {
     }
     int expand(const int32_t* idx, int cnt, const uint8_t* player, int bar_null, int finalize, int time_ms, int kmax, int lmax, int32_t* K,
                uint8_t* keys, uint8_t* key_len, uint8_t* field, uint8_t* vec, uint8_t* pidx, int8_t* reward, uint8_t* done,
-               uint8_t* lines) override {
+               uint8_t* lines, uint8_t* dead) override {
         Game<G, 1> g; bind(g);
         std::vector<uint32_t> lst((size_t)(kmax + 1) * KW);
         int nbad = 0;
@@ -246,6 +246,7 @@ template <int H, int W> struct HS : HSBase {
                 if (reward) reward[o] = (int8_t)r;
                 if (done) done[o] = d;
                 if (lines) { lines[2 * o] = (uint8_t)g.p[0].reward; lines[2 * o + 1] = (uint8_t)g.p[1].reward; }
+                if (dead) { dead[2 * o] = (uint8_t)g.p[0].dead; dead[2 * o + 1] = (uint8_t)g.p[1].dead; }
                 obs_of(g, field ? field + o * 2 * H * W : nullptr, vec ? vec + o * 2 * VEC_LEN : nullptr, pidx ? pidx + 2 * o : nullptr);
             }
         }
@@ -315,8 +316,8 @@ int hs_enumerate(void* h, const int32_t* idx, int n, const uint8_t* player, int 
 }
 int hs_expand(void* h, const int32_t* idx, int n, const uint8_t* player, int bar_null, int finalize, int time_ms, int kmax, int lmax,
               int32_t* K, uint8_t* keys, uint8_t* key_len, uint8_t* field, uint8_t* vec, uint8_t* pidx, int8_t* reward, uint8_t* done,
-              uint8_t* lines) {
-    return ((HSBase*)h)->expand(idx, n, player, bar_null, finalize, time_ms, kmax, lmax, K, keys, key_len, field, vec, pidx, reward, done, lines);
+              uint8_t* lines, uint8_t* dead) {
+    return ((HSBase*)h)->expand(idx, n, player, bar_null, finalize, time_ms, kmax, lmax, K, keys, key_len, field, vec, pidx, reward, done, lines, dead);
 }
 int hs_flags(void* h, int game) { return ((HSBase*)h)->flags(game); }
 void hs_get_game(void* h, int game, b2t_game_raw* out, uint8_t* field) { ((HSBase*)h)->get_game(game, out, field); }

@@ -36,7 +36,7 @@ def lib():
         L.hs_enumerate.restype = i32
         L.hs_enumerate.argtypes = [vp, i32p, i32, u8p, i32, i32, i32, i32p, u8p, u8p]
         L.hs_expand.restype = i32
-        L.hs_expand.argtypes = [vp, i32p, i32, u8p, i32, i32, i32, i32, i32, i32p, u8p, u8p, u8p, u8p, u8p, i8p, u8p, u8p]
+        L.hs_expand.argtypes = [vp, i32p, i32, u8p, i32, i32, i32, i32, i32, i32p, u8p, u8p, u8p, u8p, u8p, i8p, u8p, u8p, u8p]
         L.hs_get_game.argtypes = [vp, i32, vp, u8p]
         L.hs_set_game.argtypes = [vp, i32, vp, u8p]
         L.hs_copy_game.argtypes = [vp, i32, vp, i32]
@@ -112,11 +112,11 @@ class HostSimVector:
         o = dict(K=np.zeros(n, np.int32), keys=np.zeros((n, kmax, lmax), np.uint8), key_len=np.zeros((n, kmax), np.uint8),
                  reward=np.zeros((n, kmax), np.int8), done=np.zeros((n, kmax), np.uint8), lines=np.zeros((n, kmax, 2), np.uint8),
                  field=np.zeros((n, kmax, 2, self.H, self.W), np.uint8), vec=np.zeros((n, kmax, 2, 19), np.uint8),
-                 piece_idx=np.zeros((n, kmax, 2), np.uint8))
+                 piece_idx=np.zeros((n, kmax, 2), np.uint8), dead=np.zeros((n, kmax, 2), np.uint8))
         o["bad"] = lib().hs_expand(self.h, _p(idx, C.c_int32), n, _p(player, C.c_uint8), int(bar_null_moves), int(finalize), time_ms, kmax, lmax,
                                    _p(o["K"], C.c_int32), _p(o["keys"], C.c_uint8), _p(o["key_len"], C.c_uint8), _p(o["field"], C.c_uint8),
                                    _p(o["vec"], C.c_uint8), _p(o["piece_idx"], C.c_uint8), _p(o["reward"], C.c_int8), _p(o["done"], C.c_uint8),
-                                   _p(o["lines"], C.c_uint8))
+                                   _p(o["lines"], C.c_uint8), _p(o["dead"], C.c_uint8))
         return o
 
     def get_game(self, game, want_field=True):
