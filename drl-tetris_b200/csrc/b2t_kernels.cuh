@@ -253,6 +253,10 @@ __device__ __forceinline__ void emit_vecs(uint8_t* sv, const PS& p0, const PS& p
         uint16_t* d16 = reinterpret_cast<uint16_t*>(sv + lane * 2 * VEC_LEN);   // 2-byte aligned (38*lane)
 #pragma unroll
         for (int k = 0; k < 19; k++) d16[k] = (uint16_t)(r[k >> 1] >> (16 * (k & 1)));
+    } else if (lane < valid_rows) {   // an inert row inside the valid range (game id outside the handle): zeros, not stale staging bytes
+        uint16_t* d16 = reinterpret_cast<uint16_t*>(sv + lane * 2 * VEC_LEN);
+#pragma unroll
+        for (int k = 0; k < 19; k++) d16[k] = 0;
     }
     __syncwarp();
     if constexpr (DT != 0) {     // the staged bytes widened on the way out: 8 (half / bfloat16) or 4 (float) values per 128-bit store

@@ -442,8 +442,10 @@ def test_edge_cases_through_the_abi():
         Engine(0)
     assert e.value.code == _lib.ERR_ARG
     eng = Engine(5)
-    with pytest.raises(B2TError) as e:          # more rows than games
+    with pytest.raises(IndexError):             # an id outside the vector (the reference's list of envs raises the same)
         eng.reset(np.zeros(6, np.uint32), np.arange(6))
+    with pytest.raises(B2TError) as e:          # more rows than games
+        eng.reset(np.zeros(6, np.uint32), np.array([0, 1, 2, 3, 4, 0]))
     assert e.value.code == _lib.ERR_ARG
     with pytest.raises(B2TError) as e:          # placement stepping before any enumerate
         eng.step(np.zeros(5, np.uint8), placement=np.zeros(5, np.int32))
