@@ -636,8 +636,17 @@ struct EParams {
 //   3. every lane writes its top drops into the remaining slots.
 // Emission order is exactly TestField::getMask's: combos ascending (x-major, rotation-minor), top drop first, then the
 // combo's cavities by increasing height.
-constexpr int ETPB = 64;              // threads per block of the enumerate kernel (small: 65 536 boards must still fill 148 SMs)
-constexpr int EWARPS = ETPB / 32;
+constexpr int EWARPS = 2;             // warps per block that OWN boards (small: 65 536 boards must still fill 148 SMs)
+#ifndef B2T_ENUM_HELPERS
+#define B2T_ENUM_HELPERS 1
+#endif
+// Helper warps.  65 536 boards are only 2 048 owner warps — 3.5 per scheduler — and the pooled search is one long chain of dependent
+// integer instructions, so the kernel ran at the speed of its instruction latencies (issue slots 36 % used).  Every owner warp
+// therefore gets EHELP helper warps that carry no boards and only pull candidates from the owner's pool during phase 2 (pairwise
+// named barriers around each pooled search); the registers are capped so that owners and helpers of all boards are resident at once.
+constexpr int EHELP = B2T_ENUM_HELPERS;
+constexpr int ETPB = 32 * EWARPS * (1 + EHELP);   // threads per block of the enumerate kernel
+constexpr int EMINB = 28 / (ETPB / 32) < 1 ? 1 : 28 / (ETPB / 32);   // resident blocks the register cap is chosen for (28 warps per SM)
 #ifndef B2T_ENUM_BPW
 #define B2T_ENUM_BPW 32
 #endif
@@ -663,7 +672,8 @@ template <class G> struct EnumCfg {
     static constexpr int O_INCL = O_RES + EWARPS * RES * RSW * 4;
     static constexpr int O_Q = O_INCL + EWARPS * 32 * 4;
     static constexpr int O_KIND = O_Q + EWARPS * 4 + ((EWARPS & 1) ? 4 : 0);
-    static constexpr int O_TAB = O_KIND + ENB * 4;
+    static constexpr int O_CTL = O_KIND + ENB * 4;                   // [EWARPS][2] {entries of the group (-1: no more work), first entry} for the helpers
+    static constexpr int O_TAB = O_CTL + EWARPS * 8;
     static constexpr int O_ACC = O_TAB + 128;
     static constexpr int O_PBUF = ((O_ACC + ACAP * ENB + 15) / 16) * 16;
     static constexpr int SMEM = O_PBUF + G::KEYW * ENB * 4 + 16;   // O_PBUF: per-thread scratch for the sequence being accepted
@@ -682,7 +692,7 @@ __device__ __forceinline__ int rank128(uint64_t lo, uint64_t hi, int nbits) {  /
 }
 
 template <class G>
-__global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
+__global__ void __launch_bounds__(ETPB, EMINB) enumerate_kernel(const EParams p) {
     typedef typename G::col_t col_t;
     typedef EnumCfg<G> C;
     constexpr int KW = G::KEYW;
@@ -693,12 +703,15 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
     uint32_t* s_res = reinterpret_cast<uint32_t*>(smem + C::O_RES);     // [EWARPS][RES][RSW] header + raw path of every pooled search
     int* s_incl = reinterpret_cast<int*>(smem + C::O_INCL);             // [EWARPS][32] inclusive candidate counts
     int* s_q = reinterpret_cast<int*>(smem + C::O_Q);                   // [EWARPS] work-queue heads
-    int* s_kind = reinterpret_cast<int*>(smem + C::O_KIND);             // [ETPB]
+    int* s_kind = reinterpret_cast<int*>(smem + C::O_KIND);             // [ENB]
+    volatile int* s_ctl = reinterpret_cast<volatile int*>(smem + C::O_CTL);
     uint16_t* s_tab = reinterpret_cast<uint16_t*>(smem + C::O_TAB);
     uint8_t* s_acc = smem + C::O_ACC;                                   // [ACAP][ETPB] combo of every accepted finesse entry
     uint32_t* s_seq = reinterpret_cast<uint32_t*>(smem + C::O_PBUF);    // [KW][ETPB] key string being accepted by this owner
-    const int tid0 = threadIdx.x, lane = tid0 & 31, warp = tid0 >> 5;
-    const bool has = lane < BPW;                        // this lane carries a board
+    const int tid0 = threadIdx.x, lane = tid0 & 31, wid = tid0 >> 5;
+    const bool helper = wid >= EWARPS;                  // helper warps own no boards: they only search
+    const int warp = helper ? (wid - EWARPS) % EWARPS : wid;   // the pool this warp works on (= index of the owner warp)
+    const bool has = !helper && lane < BPW;             // this lane carries a board
     const int tid = warp * BPW + (has ? lane : 0);      // board slot in the block's shared arrays (idle lanes alias slot 0, read-only)
     const int i = blockIdx.x * ENB + tid;
     if (tid0 < 28) { s_tab[tid0] = p.tabs.pcn[tid0]; s_tab[32 + tid0] = p.tabs.pcc[tid0]; }
@@ -750,6 +763,62 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
     Enumerator<G, ENB, KW, NoSink, 1> e(b, tb, kk, ns, nullptr);
     __syncwarp();
 
+    // the owner warp of a pool and its helpers meet at a named barrier before and after every pooled search
+    auto pool_barrier = [&]() {
+        static_assert(EWARPS <= 2, "one named barrier per pool: add cases");
+        if (EHELP == 0) __syncwarp();
+        else if (warp == 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * (1 + EHELP)) : "memory");      // immediate ids: the kernel reserves 3 barriers, not 16
+        else asm volatile("bar.sync 2, %0;" ::"n"(32 * (1 + EHELP)) : "memory");
+    };
+    // phase 2 proper: every lane pulls the pool's next candidate as soon as its search ends; all busy lanes step together
+    auto pool_search = [&](int g0, int n_g) {
+        bool busy = false;
+        int myj = 0;
+        for (;;) {
+            if (!busy) {
+                const int j = atomicAdd(&s_q[warp], 1);
+                if (j < n_g) {
+                    const int g = g0 + j;
+                    int o = 0;   // owner = first lane whose inclusive count exceeds g
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) {
+                        const int t = o + step;
+                        if (t <= 31 && s_incl[warp * 32 + t - 1] <= g) o = t;
+                    }
+                    const int o_excl = o ? s_incl[warp * 32 + o - 1] : 0;
+                    const int otid = warp * BPW + o;
+                    const uint32_t cd = s_cand[(g - o_excl) * ENB + otid];
+                    Board<G, ENB> ob;
+                    ob.cols = s_cols + otid;
+                    ob.stream = nullptr;
+                    const int okind = s_kind[otid];
+                    e.rebind(ob, okind, spawn_rot_of(tb, okind), s_pc4[2 * otid], s_pc4[2 * otid + 1]);
+                    e.pbuf = reinterpret_cast<uint8_t*>(s_res + (warp * C::RES + j) * C::RSW + 1);   // the path is built in the result slot
+                    e.path_clear();
+                    e.search_begin((int)(cd >> 10) - 1, (int)(cd & 63u), (int)((cd >> 6) & 3u));
+                    busy = true;
+                    myj = j;
+                }
+            }
+            if (__all_sync(0xFFFFFFFFu, !busy)) break;
+            if (busy && e.search_step()) {
+                s_res[(warp * C::RES + myj) * C::RSW] = e.found
+                    ? (0x80000000u | ((uint32_t)e.path_n << 16) | ((uint32_t)((e.best_x + 8) & 255) << 8) | ((uint32_t)e.best_rot << 2) | (e.path_bad ? 1u : 0u))
+                    : 0u;
+                busy = false;
+            }
+        }
+    };
+    if (helper) {            // helpers: wait for a group of the owner's candidates, search it with the owner, repeat until told to leave
+        for (;;) {
+            pool_barrier();
+            const int n_g = s_ctl[2 * warp], g0 = s_ctl[2 * warp + 1];
+            if (n_g < 0) return;
+            pool_search(g0, n_g);
+            pool_barrier();
+        }
+    }
+
     int c_next = 0;
     while (c_next < C::NCOMBO) {
         // ---- phase 1: my combos, until some lane could run out of candidate slots
@@ -791,45 +860,10 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
         __syncwarp();
         for (int g0 = 0; g0 < total; g0 += C::RES) {
             const int n_g = (total - g0) < C::RES ? (total - g0) : C::RES;
-            if (lane == 0) s_q[warp] = 0;
-            __syncwarp();
-            bool busy = false;
-            int myj = 0;
-            for (;;) {
-                if (!busy) {
-                    const int j = atomicAdd(&s_q[warp], 1);
-                    if (j < n_g) {
-                        const int g = g0 + j;
-                        int o = 0;   // owner = first lane whose inclusive count exceeds g
-#pragma unroll
-                        for (int step = 16; step >= 1; step >>= 1) {
-                            const int t = o + step;
-                            if (t <= 31 && s_incl[warp * 32 + t - 1] <= g) o = t;
-                        }
-                        const int o_excl = o ? s_incl[warp * 32 + o - 1] : 0;
-                        const int otid = warp * BPW + o;
-                        const uint32_t cd = s_cand[(g - o_excl) * ENB + otid];
-                        Board<G, ENB> ob;
-                        ob.cols = s_cols + otid;
-                        ob.stream = nullptr;
-                        const int okind = s_kind[otid];
-                        e.rebind(ob, okind, spawn_rot_of(tb, okind), s_pc4[2 * otid], s_pc4[2 * otid + 1]);
-                        e.pbuf = reinterpret_cast<uint8_t*>(s_res + (warp * C::RES + j) * C::RSW + 1);   // the path is built in the result slot
-                        e.path_clear();
-                        e.search_begin((int)(cd >> 10) - 1, (int)(cd & 63u), (int)((cd >> 6) & 3u));
-                        busy = true;
-                        myj = j;
-                    }
-                }
-                if (__all_sync(0xFFFFFFFFu, !busy)) break;
-                if (busy && e.search_step()) {
-                    s_res[(warp * C::RES + myj) * C::RSW] = e.found
-                        ? (0x80000000u | ((uint32_t)e.path_n << 16) | ((uint32_t)((e.best_x + 8) & 255) << 8) | ((uint32_t)e.best_rot << 2) | (e.path_bad ? 1u : 0u))
-                        : 0u;
-                    busy = false;
-                }
-            }
-            __syncwarp();
+            if (lane == 0) { s_q[warp] = 0; s_ctl[2 * warp] = n_g; s_ctl[2 * warp + 1] = g0; }
+            pool_barrier();          // the helpers see this group (and the candidates, counts and boards written above)
+            pool_search(g0, n_g);
+            pool_barrier();          // every search of the group has left its result
             // ---- collect: I am the owner of group entries [a, bnd)
             int a = excl - g0, bnd = incl - g0;
             a = a < 0 ? 0 : a; bnd = bnd > n_g ? n_g : bnd;
@@ -874,6 +908,10 @@ __global__ void __launch_bounds__(ETPB) enumerate_kernel(const EParams p) {
             }
             __syncwarp();
         }
+    }
+    if (EHELP > 0) {         // no more groups: the helpers leave
+        if (lane == 0) s_ctl[2 * warp] = -1;
+        pool_barrier();
     }
     // ---- phase 3: top drops
     if (active) {
