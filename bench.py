@@ -430,6 +430,32 @@ def main():
     achieved = STEP_BYTES * n / (k_ms * 1e-3) / 1e9
     stats = sharding.reduce_stats(eng.stats(), device=dev)    # the only collective: end-of-rollout episode counters
 
+    def traffic_probe():
+        """b2t_debug_traffic: one launch with the HBM traffic of a fused step (same tiles, same coalesced accesses, same resident
+        warps) and no game logic — the bandwidth this read/write mix reaches on this device, next to the plain-copy peak."""
+        import ctypes as C
+        P = lambda t: C.c_void_p(t.data_ptr())
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        snap = eng.export_states(np.arange(0, n, max(1, n // 64), dtype=np.int32))   # (the probe scribbles on the games)
+        eng.snapshot(3)
+        def go():
+            rc = eng.lib.b2t_debug_traffic(eng._h, n, P(keys_r[0]), keys_r[0].shape[1], P(player_r[0]), P(len_r[0]), P(seed_r[0]), P(reward), P(done),
+                                           P(lines), P(field), P(vec), P(pidx), 1, st)
+            assert rc == 0
+        for _ in range(3):
+            go()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a0.record()
+        for _ in range(10):
+            go()
+        a1.record()
+        torch.cuda.synchronize()
+        eng.restore(3)
+        torch.cuda.synchronize()
+        assert np.array_equal(snap, eng.export_states(np.arange(0, n, max(1, n // 64), dtype=np.int32)))
+        return a0.elapsed_time(a1) / 10
+
     out = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": total_ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
            "data": "synthetic",
@@ -438,6 +464,13 @@ def main():
            "roofline": {"bound": "hbm", "kernel": "game_kernel<22,10> (fused step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "peak_source": peak_src, "algorithmic_bytes_per_env_step": STEP_BYTES,
                         "launch_ms": k_ms, "traffic": ncu_traffic("step_bytes_per_launch")}}
+    if not a.no_extras and a.leg in ("all", "step") and not a.cuda_profile:
+        p_ms = traffic_probe()
+        out["roofline"]["mix_peak"] = {"achieved": STEP_BYTES * n / (p_ms * 1e-3) / 1e9, "unit": "GB/s", "launch_ms": p_ms,
+                                       "frac_of_mix_peak": p_ms / k_ms,
+                                       "note": "b2t_debug_traffic: the step's own reads and writes (tiles, coalesced 128-bit accesses, 16 resident "
+                                               "warps per SM) with no game logic; what is left between it and the step is game logic that does "
+                                               "not overlap the memory traffic"}
 
     if a.leg == "step":
         a.no_extras = True

@@ -92,6 +92,7 @@ SYMBOLS = {
                                   u8p, u8p, C.c_int32, i8p, u8p, u8p, u8p, u8p, u8p, i32p]),
     "b2t_host_alloc": (C.c_int, [C.c_size_t, C.c_int32, C.POINTER(vp)]),
     "b2t_host_free": (C.c_int, [vp]),
+    "b2t_debug_traffic": (C.c_int, [vp, C.c_int32, vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int32, vp]),
     "b2t_debug_streams": (C.c_int, [vp, C.c_uint32, C.c_int32, u8p, u8p]),
 }
 

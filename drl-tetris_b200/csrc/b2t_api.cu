@@ -473,6 +473,17 @@ int b2t_host_alloc(size_t bytes, int32_t write_combined, void** out) {
 }
 int b2t_host_free(void* p) { return (!p || cudaFreeHost(p) == cudaSuccess) ? B2T_OK : B2T_ERR_CUDA; }
 
+int b2t_debug_traffic(b2t_handle* h, int32_t n, const uint8_t* d_keys, int32_t lmax, const uint8_t* d_player, const uint8_t* d_key_len,
+                      const uint32_t* d_seeds, int8_t* d_reward, uint8_t* d_done, uint8_t* d_lines, uint8_t* d_field, uint8_t* d_vec,
+                      uint8_t* d_piece_idx, int32_t step_like, void* stream) {
+    if (!h || n < 0 || n > h->cfg.n_games || !d_keys || !d_player || !d_key_len || !d_seeds || !d_reward || !d_done || !d_lines || !d_field ||
+        !d_vec || !d_piece_idx) return fail(h, B2T_ERR_ARG, "b2t_debug_traffic: every array is required%s");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(h->ops->launch_traffic(h->state, n, d_keys, lmax, d_player, d_key_len, d_seeds, d_reward, d_done, d_lines, d_field, d_vec, d_piece_idx,
+                              step_like, (cudaStream_t)stream));
+    return B2T_OK;
+}
+
 int b2t_debug_streams(b2t_handle* h, uint32_t seed16, int32_t n, uint8_t* h_pieces, uint8_t* h_holes) {
     if (!h || seed16 >= (uint32_t)RNG_SEEDS || n < 0) return B2T_ERR_ARG;
     CK(cudaSetDevice(h->cfg.device));

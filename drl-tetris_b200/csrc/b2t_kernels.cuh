@@ -1152,6 +1152,44 @@ __global__ void copy_game_kernel(uint4* dst_state, int dst, const uint4* src_sta
 
 #endif  // B2T_COMMON_KERNELS
 
+// ---------------------------------------------------------------------------------------------- traffic probe
+// The HBM traffic of one fused step and nothing else: every thread reads its game's NV vectors and its key row, writes the vectors
+// back and the warp writes 32 rows of observation bytes, with the step kernel's own access pattern (tiles, coalesced 128-bit
+// accesses), block size and shared-memory footprint (so the same number of warps is resident), but no game logic.  Its bandwidth is
+// what this read/write mix can reach on the device — the practical ceiling the step kernel is compared with next to the plain
+// copy peak (bench.py: roofline.mix_peak).  Measurement aid only: b2t_debug_traffic.
+template <class G>
+__global__ void __launch_bounds__(TPB, B2T_GAME_MINB) traffic_kernel(uint4* state, int n, const uint8_t* keys, int lmax, const uint8_t* player,
+                                                                     const uint8_t* key_len, const uint32_t* seeds, int8_t* reward, uint8_t* done,
+                                                                     uint8_t* lines, uint8_t* field, uint8_t* vec, uint8_t* piece_idx) {
+    constexpr int HW = G::H * G::W;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row = blockIdx.x * TPB + tid;
+    const int warp_row0 = blockIdx.x * TPB + warp * 32;
+    if (warp_row0 + 32 > n) return;                    // whole warps only: the probe is about bandwidth, not edges
+    uint4 q[G::NV];
+    const uint4* src = state + state_index<G>(row, 0);
+#pragma unroll
+    for (int v = 0; v < G::NV; v++) q[v] = src[v * 32];
+    uint32_t x = player[row] + key_len[row] + seeds[row];
+    if (lmax == 16) { const uint4 k = *reinterpret_cast<const uint4*>(keys + (size_t)row * 16); x += k.x ^ k.y ^ k.z ^ k.w; }
+#pragma unroll
+    for (int v = 0; v < G::NV; v++) x += q[v].x ^ q[v].w;
+    reinterpret_cast<uint32_t*>(smem)[tid] = x;        // keeps the loads alive without touching the stored values
+    uint4* dst = state + state_index<G>(row, 0);
+#pragma unroll
+    for (int v = 0; v < G::NV; v++) { q[v].y += 1u; dst[v * 32] = q[v]; }   // (modified: a store of the value just loaded would be elided)
+    reward[row] = (int8_t)(x & 1); done[row] = (uint8_t)((x >> 1) & 1);
+    *reinterpret_cast<uint16_t*>(lines + 2 * (size_t)row) = (uint16_t)x;
+    *reinterpret_cast<uint16_t*>(piece_idx + 2 * (size_t)row) = (uint16_t)(x >> 3);
+    const uint4 fill = make_uint4(x & 0x01010101u, (x >> 1) & 0x01010101u, (x >> 2) & 0x01010101u, (x >> 3) & 0x01010101u);
+    uint4* of = reinterpret_cast<uint4*>(field + (size_t)warp_row0 * (2 * HW));
+    for (int c = lane; c < 4 * HW; c += 32) of[c] = fill;                       // 32 rows x 2*HW bytes = 4*HW chunks of 16 bytes
+    uint4* ov = reinterpret_cast<uint4*>(vec + (size_t)warp_row0 * (2 * VEC_LEN));
+    for (int c = lane; c < 32 * 2 * VEC_LEN / 16; c += 32) ov[c] = fill;
+}
+
 // ---------------------------------------------------------------------------------------------- per-geometry launch table
 struct GeomOps {
     int H, W, NV, KMAX, KEYW, LMAX, smem_game, smem_enum;
@@ -1160,6 +1198,8 @@ struct GeomOps {
     cudaError_t (*launch_enum)(const EParams&, cudaStream_t);
     cudaError_t (*launch_unpack)(const uint32_t*, const int32_t*, const int32_t*, int, int, int, int, uint8_t*, uint8_t*, cudaStream_t);
     cudaError_t (*launch_init)(uint4*, int, cudaStream_t);
+    cudaError_t (*launch_traffic)(uint4*, int, const uint8_t*, int, const uint8_t*, const uint8_t*, const uint32_t*, int8_t*, uint8_t*, uint8_t*,
+                                  uint8_t*, uint8_t*, uint8_t*, int, cudaStream_t);
     void (*decode)(const uint32_t* words, b2t_game_raw* out, uint8_t* field, const uint32_t* planes);          // host codec, b2t_raw.cuh
     void (*encode)(uint32_t* words, const b2t_game_raw* in, const uint8_t* field, uint32_t* planes);
     int tile_words;               // colour-plane words per game: 2 * TILE_PLANES * SW
@@ -1175,6 +1215,8 @@ template <class G> struct Launch {
         e = cudaFuncSetAttribute(game_kernel<G, GM_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::GAME_TOTAL);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(enumerate_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, EnumCfg<G>::SMEM);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(traffic_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::GAME_TOTAL);
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(init_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::GAME_TOTAL);
     }
@@ -1204,9 +1246,17 @@ template <class G> struct Launch {
         init_kernel<G><<<(n + TPB - 1) / TPB, TPB, L::GAME_TOTAL, s>>>(state, n);
         return cudaGetLastError();
     }
+    static cudaError_t traffic(uint4* state, int n, const uint8_t* keys, int lmax, const uint8_t* player, const uint8_t* key_len,
+                               const uint32_t* seeds, int8_t* reward, uint8_t* done, uint8_t* lines, uint8_t* field, uint8_t* vec,
+                               uint8_t* piece_idx, int step_like, cudaStream_t s) {
+        // step_like: the step kernel's shared-memory footprint, i.e. its 16 resident warps per SM; otherwise as many as the registers allow
+        traffic_kernel<G><<<(n + TPB - 1) / TPB, TPB, step_like ? L::GAME_TOTAL : TPB * 4, s>>>(state, n, keys, lmax, player, key_len, seeds, reward, done, lines,
+                                                                            field, vec, piece_idx);
+        return cudaGetLastError();
+    }
     static const GeomOps* ops() {
         static const GeomOps o = {G::H, G::W, G::NV, G::KMAX, G::KEYW, G::LMAX, L::GAME_TOTAL, EnumCfg<G>::SMEM,
-                                  &prepare, &game, &enumerate, &unpack, &init, &decode_game<G>, &encode_game<G>, 2 * TILE_PLANES * G::SW};
+                                  &prepare, &game, &enumerate, &unpack, &init, &traffic, &decode_game<G>, &encode_game<G>, 2 * TILE_PLANES * G::SW};
         return &o;
     }
 };

@@ -274,6 +274,15 @@ int b2t_expand_host(b2t_handle *h, const int32_t *h_game_idx, int32_t n, const u
 int b2t_host_alloc(size_t bytes, int32_t write_combined, void **out);
 int b2t_host_free(void *p);
 
+/* Measurement aid (bench.py roofline.mix_peak): one launch with exactly the HBM traffic of a fused b2t_step of games 0..n-1 — state
+ * vectors read and written back with one word changed (the handle's games are garbage afterwards), key rows / players / lengths / seeds read, reward / done / lines / observation tensors
+ * written with arbitrary bytes — and no game logic: the bandwidth this read/write mix reaches on the device.  All pointers are
+ * device pointers shaped as in b2t_step_args (d_keys [n,lmax]); the caller's output arrays are overwritten with garbage.
+ * step_like != 0: with the step kernel's shared-memory footprint (its 16 resident warps per SM); 0: as many warps as fit. */
+int b2t_debug_traffic(b2t_handle *h, int32_t n, const uint8_t *d_keys, int32_t lmax, const uint8_t *d_player,
+                      const uint8_t *d_key_len, const uint32_t *d_seeds, int8_t *d_reward, uint8_t *d_done, uint8_t *d_lines,
+                      uint8_t *d_field, uint8_t *d_vec, uint8_t *d_piece_idx, int32_t step_like, void *stream);
+
 /* Stream-table probe for tests: first n entries of the piece / hole stream of a 16-bit seed. */
 int b2t_debug_streams(b2t_handle *h, uint32_t seed16, int32_t n, uint8_t *h_pieces, uint8_t *h_holes);
 

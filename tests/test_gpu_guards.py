@@ -156,3 +156,25 @@ def test_pinned_but_misaligned_host_buffers_take_the_staged_path():
         for x, y in zip(ra, rb):
             assert np.array_equal(x, y)
     assert np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_traffic_probe_runs_and_only_scribbles_on_its_own_handle():
+    """b2t_debug_traffic (measurement aid of bench.py): B2T_OK, argument errors reported, the device stays healthy."""
+    import torch
+    e = _fresh(4096)
+    dev = torch.device("cuda:0")
+    n = e.n
+    P = lambda t: C.c_void_p(t.data_ptr())
+    keys = torch.zeros((n, 16), dtype=torch.uint8, device=dev); b1 = torch.zeros(n, dtype=torch.uint8, device=dev)
+    seeds = torch.zeros(n, dtype=torch.int32, device=dev); rew = torch.empty(n, dtype=torch.int8, device=dev)
+    lines = torch.empty((n, 2), dtype=torch.uint8, device=dev); pidx = torch.empty((n, 2), dtype=torch.uint8, device=dev)
+    field = torch.empty((n, 2, 22, 10), dtype=torch.uint8, device=dev); vec = torch.empty((n, 2, 19), dtype=torch.uint8, device=dev)
+    for mode in (1, 0):
+        assert e.lib.b2t_debug_traffic(e._h, n, P(keys), 16, P(b1), P(b1), P(seeds), P(rew), P(b1.clone()), P(lines), P(field), P(vec), P(pidx), mode, None) == 0
+    assert e.lib.b2t_debug_traffic(e._h, n + 1, P(keys), 16, P(b1), P(b1), P(seeds), P(rew), P(b1), P(lines), P(field), P(vec), P(pidx), 1, None) == -1
+    assert e.lib.b2t_debug_traffic(e._h, n, None, 16, P(b1), P(b1), P(seeds), P(rew), P(b1), P(lines), P(field), P(vec), P(pidx), 1, None) == -1
+    torch.cuda.synchronize()
+    e.reset(harness.seeds_for(np.arange(n), np.zeros(n, int)))      # the handle is usable again after a reset
+    K, _, _ = e.enumerate(np.zeros(n, np.uint8), want_keys=False)
+    assert (K > 1).all()
+    e.close()
