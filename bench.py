@@ -141,16 +141,16 @@ def workload_config(n):
 
 
 # ---------------------------------------------------------------------------------------------- CPU legs
-def cpu_port_leg(n=2048, steps=48):
+def cpu_port_leg(n=8192, steps=600):
     """The plain-C oracle (oracle/tetris_oracle.c) on ONE host core, same workload S on a bounded sample."""
     import pyoracle
     v = pyoracle.OracleVector(n, H, W)
     gids = np.arange(n)
     v.reset((splitmix64(0xB200, gids, 0) & np.uint64(0xFFFF)).astype(np.uint32))
-    pre = [sventon_keys(gids, t) for t in range(steps)]
+    pre = [sventon_keys(gids, t) for t in range(64)]      # a ring of pre-generated key strings, as on the GPU side
     t0 = time.perf_counter()
     for t in range(steps):
-        keys, ln = pre[t]
+        keys, ln = pre[t % 64]
         _, done, _ = v.step(((gids + t) & 1).astype(np.uint8), keys, ln)
         v.observe()
         d = np.nonzero(done)[0]
@@ -173,11 +173,11 @@ def _ref_worker(args):
         h = mod.PythonHandle(2, [H, W])
         h.reset()
         hs.append(h)
-    pre = [sventon_keys(gids, t) for t in range(steps)]
+    pre = [sventon_keys(gids, t) for t in range(min(steps, 64))]     # a ring of pre-generated key lists
     pre = [[[int(k) for k in keys[i, :ln[i]]] for i in range(n)] for keys, ln in pre]
     t0 = time.perf_counter()
     for t in range(steps):
-        acts = pre[t]
+        acts = pre[t % len(pre)]
         for i, h in enumerate(hs):
             p = (int(gids[i]) + t) & 1
             a = [[0], [0]]
@@ -235,7 +235,7 @@ def _ref_world_model_worker(args):
     return placements, time.perf_counter() - t0
 
 
-def reference_leg(steps, per_proc_games=256, per_proc_steps=200):
+def reference_leg(steps, per_proc_games=256, per_proc_steps=800):
     """The reference's own C++ backend (unmodified, compiled -O2 into oracle/_ref/B) on every host core."""
     import multiprocessing as mp
     import refmod
@@ -477,7 +477,7 @@ def main():
     if not a.no_extras and a.leg == "all":
         # ---- end-to-end through the C ABI with HOST buffers (b2t_step_host): H2D of the step's inputs, D2H of reward/done and
         # of the observation tensors, inside the timed region
-        e2e_steps = max(2, min(a.steps, 10))
+        e2e_steps = max(2, min(a.steps, 30))
         import ctypes as C
         from b200tetris.engine import _hp
         def pinned(t):   # numpy view of a pinned host copy of a device tensor
