@@ -595,12 +595,28 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms_nf = e0.elapsed_time(e1) / reps
+        # extra format (not the graded figure): fields as bits, [rows, 2, ceil(H*W/32)] words instead of [rows, 2, H, W] bytes
+        pfb = torch.empty((cap, 2, (H * W + 31) // 32), dtype=torch.int32, device=dev)
+
+        def expand_bits():
+            w.expand_dev(side, K, offs, cap, board=pb, keys=pk, key_len=pl_, reward=pr, done=pd, field=pfb, vec=pv, piece_idx=pp)
+        for _ in range(2):
+            expand_bits()
+        e0.record()
+        for _ in range(reps):
+            expand_bits()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_bits = e0.elapsed_time(e1) / reps
+        del pfb
         mean_k = total / nb
         ach = board_bytes(mean_k) * nb / (ms * 1e-3) / 1e9
         out["placements"] = {"metric": "placements_per_sec", "value": total * world / (ms * 1e-3), "unit": "placements/s",
                              "boards_per_sec": nb * world / (ms * 1e-3), "boards_per_gpu": nb, "mean_K": mean_k, "ms_per_expand": ms,
                              "finalize": True, "gpu_launches_per_expand": 6,
                              "finalize_false": {"value": total * world / (ms_nf * 1e-3), "ms_per_expand": ms_nf},
+                             "bit_packed_fields": {"value": total * world / (ms_bits * 1e-3), "ms_per_expand": ms_bits,
+                                                   "note": "extra format b2t_obs.dtype = B2T_BITS (one bit per cell); single-GPU timing"},
                              "workload": "C3 (BASELINE configs[2]): %d boards after 8..40 plies of random placements; enumerate + scan + "
                                          "expand(finalize=1) with uint8 tensors, keys, reward, done for every placement" % nb,
                              "roofline": {"bound": "hbm", "kernel": "enumerate_kernel + game_kernel<22,10> (expand)", "achieved": ach, "peak": peak,
@@ -641,6 +657,49 @@ def main():
                                          "with engine-chosen reset seeds; no host data, one graph launch (b200tetris.ActorLoop). "
                                          "SURVEY.md 8d: step + uint8 world model is 14.1 KB per env-step, an HBM ceiling of 4.6e8/s per GPU."}
             al.close()
+            # ---- the world model on boards of sensible play: the C3 boards above come from RANDOM placements (holes and overhangs
+            # everywhere, 9 under-overhang candidates per board for the enumerator to search); a learning agent's boards are cleaner.
+            # 40 untimed plies of a hand-made heuristic policy (low, flat, hole-free stacks; torch ops standing in for the network),
+            # then the same expand call timed on those boards.
+            sp = Engine(nb, H, W, device=local, seed=11 + rank)
+            sp.reset_dev(torch.from_numpy((splitmix64(0x5E1F, bg, 0) & np.uint64(0xFFFF)).astype(np.int64)).to(dev).to(torch.int32))
+
+            def heuristic(f, v, p, scores):
+                occ = f[:, 0].to(torch.float16)
+                filled_above = (occ.cumsum(1) > 0).to(torch.float16)
+                heights = filled_above.sum(1)
+                holes = (filled_above - occ).sum((1, 2))
+                scores.copy_((-0.5 * heights.sum(1) - 0.4 * (heights[:, 1:] - heights[:, :-1]).abs().sum(1) - 5.0 * holes).float())
+            lp = ActorLoop(sp, heuristic, use_graph=False)
+            for _ in range(40):
+                lp.step()
+            torch.cuda.synchronize()
+            del lp
+            side2 = torch.from_numpy(((bg + 40) & 1).astype(np.uint8)).to(dev)
+
+            def expand2():
+                sp.expand_dev(side2, K, offs, cap, board=pb, keys=pk, key_len=pl_, reward=pr, done=pd, field=pf, vec=pv, piece_idx=pp)
+            for _ in range(3):
+                expand2()
+            torch.cuda.synchronize()
+            total2 = int(offs[-1].item())
+            e0.record()
+            for _ in range(reps):
+                expand2()
+            e1.record()
+            torch.cuda.synchronize()
+            ms2 = e0.elapsed_time(e1) / reps
+            st2 = torch.tensor([ms2], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(st2, op=dist.ReduceOp.MAX)
+            ms2 = float(st2.item())
+            mk2 = total2 / nb
+            out["placements"]["selfplay_boards"] = {
+                "value": total2 * world / (ms2 * 1e-3), "unit": "placements/s", "boards_per_sec": nb * world / (ms2 * 1e-3), "mean_K": mk2,
+                "ms_per_expand": ms2, "roofline_frac": board_bytes(mk2) * nb / (ms2 * 1e-3) / 1e9 / peak,
+                "workload": "the same call on %d boards after 40 plies of a heuristic policy (low, flat, hole-free stacks) instead of "
+                            "random placements" % nb}
+            sp.close()
         if a.leg == "all" and world == 1:
             # ---- BASELINE configs[4]: custom field sizes and piece sets at 2^18 games
             out["custom_sizes"] = [c5_leg(torch, Engine, dev, local, rank, 16, 8, (0, 6), 1 << 18, 1 << 15, peak, min(a.steps, 10)),

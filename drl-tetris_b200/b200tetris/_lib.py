@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B2T_LIB") or os.path.join(_HERE, "libb200tetris.so")   # B2T_LIB: experimental builds (build.py --out)
 
 VEC_LEN = 19
-U8, F16, BF16, F32 = 0, 1, 2, 3   # b2t_dtype
+U8, F16, BF16, F32, BITS = 0, 1, 2, 3, 4   # b2t_dtype
 FLAG_TILES = 1                    # b2t_config.flags
 KEYS_U8, KEYS_PACKED4 = 0, 1      # b2t_step_args.key_format
 SNAPSHOT_SLOTS = 4

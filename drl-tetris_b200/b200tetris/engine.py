@@ -272,6 +272,10 @@ class Engine:
     def _dtype_of(field, vec):
         """b2t_dtype from the torch dtype of the field / vec tensors (they must agree)"""
         import torch
+        if field is not None and field.dtype == torch.int32:     # B2T_BITS: field [rows, 2, SW] int32 bit words, vec stays uint8
+            if vec is not None and vec.dtype != torch.uint8:
+                raise ValueError("with a bit-packed field (int32) vec must be uint8")
+            return _lib.BITS
         codes = {torch.uint8: _lib.U8, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16, torch.float32: _lib.F32}
         kinds = {codes[t.dtype] for t in (field, vec) if t is not None}
         if len(kinds) > 1:

@@ -228,7 +228,7 @@ static void base_params(b2t_handle* h, KParams& p) {
 static int check_obs(b2t_handle* h, const b2t_obs& o) {
     if (!aligned16(o.d_field) || !aligned16(o.d_vec) || !aligned16(o.d_piece_idx) || !aligned16(o.d_scalars))
         return fail(h, B2T_ERR_ARG, "observation pointers must be 16-byte aligned%s");
-    if (o.dtype < B2T_U8 || o.dtype > B2T_F32) return fail(h, B2T_ERR_ARG, "b2t_obs.dtype must be B2T_U8, B2T_F16, B2T_BF16 or B2T_F32%s");
+    if (o.dtype < B2T_U8 || o.dtype > B2T_BITS) return fail(h, B2T_ERR_ARG, "b2t_obs.dtype must be B2T_U8, B2T_F16, B2T_BF16, B2T_F32 or B2T_BITS%s");
     return B2T_OK;
 }
 static void set_obs(KParams& p, const b2t_obs& o) {

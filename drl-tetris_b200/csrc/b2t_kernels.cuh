@@ -76,7 +76,7 @@ struct KParams {
     uint8_t* vec;
     uint8_t* piece_idx;
     int32_t* scalars;
-    int32_t obs_dtype;            // b2t_obs.dtype of field / vec: 0 uint8, 1 half, 2 bfloat16, 3 float
+    int32_t obs_dtype;            // b2t_obs.dtype of field / vec: 0 uint8, 1 half, 2 bfloat16, 3 float, 4 fields as bits + uint8 vec
     int32_t perspective;          // 1: (me, opponent) order of the observation tensors
     const uint8_t* me;            // per-row perspective player for plain observe
     int32_t* board_of;            // KF_EXPAND
@@ -102,6 +102,7 @@ template <class G> struct SmemLayout {
     static constexpr int BITS = (((WB + 1) * 4 + 15) / 16) * 16;   // staging (aliases COLS): packed field bits of 32 rows
     static constexpr int VEC = 32 * 2 * VEC_LEN;                    // staging (aliases COLS): 32 rows x 38 bytes
     static_assert(BITS + VEC <= COLS, "output staging must fit in the warp's column area");
+    static_assert(32 * 2 * G::SW * 4 <= BITS + VEC, "B2T_BITS staging (32 rows x 2*SW words) must fit in the staging area");
     static constexpr int O_STREAM = COLS, O_KEYS = O_STREAM + STREAM, O_GQ = O_KEYS + KEYS;
     static constexpr int WARP_BYTES = ((O_GQ + GQ + 15) / 16) * 16;
     static constexpr int TAB = 64 * 2;
@@ -208,6 +209,30 @@ __device__ __forceinline__ void emit_fields(uint32_t* wb, const Board<G, WS>& b0
                 }
             }
         }
+    }
+    __syncwarp();
+}
+
+// B2T_BITS: the fields as they are kept — one bit per cell, bit row*W+col of a player's SW words — [rows, 2, SW] uint32.  An extra
+// format for consumers that unpack on the device: 8x fewer bytes than the reference's uint8 cells and no expansion work.
+template <class G>
+__device__ __forceinline__ void emit_field_bits(uint32_t* wb, const Board<G, WS>& b0, const Board<G, WS>& b1, bool has_row, uint32_t* out,
+                                                int valid_rows, int lane) {
+    constexpr int RW2 = 2 * G::SW;
+    uint32_t rec[RW2];
+#pragma unroll
+    for (int j = 0; j < G::SW; j++) { rec[j] = has_row ? b0.sw(j) : 0u; rec[G::SW + j] = has_row ? b1.sw(j) : 0u; }
+    __syncwarp();   // the staging words alias the warp's columns: every lane must be done with its board
+#pragma unroll
+    for (int j = 0; j < RW2; j++) wb[lane * RW2 + j] = rec[j];
+    __syncwarp();
+    const int total = valid_rows * RW2;                    // words
+    const uint4* s4 = reinterpret_cast<const uint4*>(wb);
+    uint4* o4 = reinterpret_cast<uint4*>(out);
+    for (int c = lane; 4 * c < total; c += 32) {
+        if (4 * c + 4 <= total) o4[c] = s4[c];
+        else
+            for (int k = 4 * c; k < total; k++) out[k] = wb[k];
     }
     __syncwarp();
 }
@@ -578,7 +603,10 @@ __global__ void __launch_bounds__(TPB, MODE == GM_EXPAND ? B2T_GAME_MINB + 1 : B
     valid_rows = valid_rows < 0 ? 0 : (valid_rows > 32 ? 32 : valid_rows);
     const Board<G, WS>& fb0 = swap ? g.b[1] : g.b[0];
     const Board<G, WS>& fb1 = swap ? g.b[0] : g.b[1];
-    if (MODE != GM_GENERIC || p.obs_dtype == 0) {      // uint8: the reference's dtype; the only one the two hot variants carry
+    if (p.obs_dtype == 4) {                            // fields as bits (B2T_BITS), vector part as uint8
+        if (p.field && valid_rows > 0) emit_field_bits<G>(s_bits, fb0, fb1, active, reinterpret_cast<uint32_t*>(p.field) + (size_t)warp_row0 * (size_t)(2 * G::SW), valid_rows, lane);
+        if (p.vec && valid_rows > 0) emit_vecs(s_vec, g.p[0], g.p[1], swap, active, p.vec + (size_t)warp_row0 * (size_t)(2 * VEC_LEN), valid_rows, lane);
+    } else if (MODE != GM_GENERIC || p.obs_dtype == 0) {      // uint8: the reference's dtype; with B2T_BITS the only ones the two hot variants carry
         if (p.field && valid_rows > 0) emit_fields<G>(s_bits, fb0, fb1, active, p.field + (size_t)warp_row0 * (size_t)(2 * L::HW), valid_rows, lane);
         if (p.vec && valid_rows > 0) emit_vecs(s_vec, g.p[0], g.p[1], swap, active, p.vec + (size_t)warp_row0 * (size_t)(2 * VEC_LEN), valid_rows, lane);
     } else if (p.obs_dtype == 3) {                     // float
@@ -1223,7 +1251,7 @@ template <class G> struct Launch {
     static cudaError_t game(const KParams& p, int rows, cudaStream_t s) {
         if (rows <= 0) return cudaSuccess;
         const dim3 grid((rows + TPB - 1) / TPB);
-        if (p.obs_dtype != 0 || p.key_fmt != 0 || p.auto_reset || ((p.flags & KF_STEP) && !p.placement && !p.key_len) ||
+        if ((p.obs_dtype != 0 && p.obs_dtype != 4) || p.key_fmt != 0 || p.auto_reset || ((p.flags & KF_STEP) && !p.placement && !p.key_len) ||
             (p.tiles && !(p.flags & KF_EXPAND))) game_kernel<G, GM_GENERIC><<<grid, TPB, L::GAME_TOTAL, s>>>(p);
         else if ((p.flags & ~KF_FINALIZE) == KF_EXPAND) game_kernel<G, GM_EXPAND><<<grid, TPB, L::GAME_TOTAL, s>>>(p);
         else if ((p.flags & ~KF_FINALIZE) == (KF_STEP | KF_STORE)) game_kernel<G, GM_STEP><<<grid, TPB, L::GAME_TOTAL, s>>>(p);

@@ -89,7 +89,7 @@ int b2t_reset(b2t_handle *h, const int32_t *d_game_idx, int32_t n, const uint32_
 
 /* Observation tensors written by step / observe / expand: the reference's state_dict for BOTH players
  * (state_processors.py:23-54; layout consumed by agents/agent_utils/state_unpack.py:88-105).  Any pointer may be NULL. */
-typedef enum { B2T_U8 = 0, B2T_F16 = 1, B2T_BF16 = 2, B2T_F32 = 3 } b2t_dtype;
+typedef enum { B2T_U8 = 0, B2T_F16 = 1, B2T_BF16 = 2, B2T_F32 = 3, B2T_BITS = 4 } b2t_dtype;
 
 typedef struct {
     void *d_field;         /* [rows, 2, H, W]  field>0 */
@@ -104,7 +104,10 @@ typedef struct {
     const uint8_t *d_me;   /* [rows], only read by b2t_observe when perspective == 1 */
     /* Element type of d_field and d_vec (b2t_dtype).  B2T_U8 is the reference's state_dict dtype; B2T_F16 / B2T_BF16 / B2T_F32
      * write the same values (exactly representable: 0/1 cells, integers <= 255) as the floating type the consumer's network
-     * takes, so no conversion pass re-reads the tensors (state_unpack.py:88-105 casts them on the host in the reference). */
+     * takes, so no conversion pass re-reads the tensors (state_unpack.py:88-105 casts them on the host in the reference).
+     * B2T_BITS is an extra, compact form for consumers that unpack on the device: d_field is uint32 [rows, 2, SW], SW = ceil(H*W/32),
+     * bit (r*W + c) % 32 of word (r*W + c) / 32 = cell (r, c) of that player's field>0 (unused high bits of the last word are 0);
+     * d_vec stays uint8.  One eighth of the bytes of the uint8 cells. */
     int32_t dtype;
 } b2t_obs;
 

@@ -178,3 +178,50 @@ def test_traffic_probe_runs_and_only_scribbles_on_its_own_handle():
     K, _, _ = e.enumerate(np.zeros(n, np.uint8), want_keys=False)
     assert (K > 1).all()
     e.close()
+
+
+@pytest.mark.parametrize("H,W,pieces", [(22, 10, (0, 1, 2, 3, 4, 5, 6)), (16, 8, (0, 6)), (40, 20, (0, 1, 2, 3, 4, 5, 6))])
+def test_bit_packed_fields_equal_the_uint8_fields(H, W, pieces):
+    """b2t_obs.dtype = B2T_BITS (an extra format): bit r*W+c of a player's SW words == the reference-shaped uint8 cell, from observe,
+    from the fused step (hot variant), from a subset step (generic variant) and from the world model, in both player orders."""
+    import torch
+    from b200tetris import Engine
+    dev = torch.device("cuda:0")
+    n = 777
+    e = Engine(n, H, W, pieces, piece_stream_len=256, hole_stream_len=64)
+    gids = np.arange(n)
+    e.reset(harness.seeds_for(gids, np.zeros(n, int)))
+    SW = (H * W + 31) // 32
+    pol = harness.Policy("junk", lmax=16)
+
+    def unpack(bits):                     # [rows, 2, SW] int32 -> [rows, 2, H, W] uint8
+        w = bits.cpu().numpy().view(np.uint32)
+        b = ((w[..., None] >> np.arange(32, dtype=np.uint32)) & 1).astype(np.uint8).reshape(w.shape[0], 2, SW * 32)
+        assert (b[..., H * W:] == 0).all()
+        return b[..., :H * W].reshape(-1, 2, H, W)
+    K = torch.empty(n, dtype=torch.int32, device=dev); offs = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    for t in range(25):
+        player = ((gids + t) & 1).astype(np.uint8)
+        keys, klen, _ = pol.choose(None, t, gids, player)
+        pl = torch.from_numpy(player).to(dev); kd = torch.from_numpy(keys).to(dev); ld = torch.from_numpy(klen).to(dev)
+        seeds = torch.from_numpy(harness.seeds_for(gids, np.full(n, t + 1)).astype(np.int64)).to(dev).to(torch.int32)
+        fb = torch.full((n, 2, SW), -1, dtype=torch.int32, device=dev); vb = torch.empty((n, 2, 19), dtype=torch.uint8, device=dev)
+        persp = bool(t & 1)
+        e.step_dev(pl, kd, ld, reset_seeds=seeds, field=fb, vec=vb, perspective=persp)          # hot variant, bits
+        f8 = torch.empty((n, 2, H, W), dtype=torch.uint8, device=dev); v8 = torch.empty((n, 2, 19), dtype=torch.uint8, device=dev)
+        e.observe_dev(field=f8, vec=v8, me=pl if persp else None)
+        fb2 = torch.full((n, 2, SW), -1, dtype=torch.int32, device=dev)
+        e.observe_dev(field=fb2, me=pl if persp else None)                                       # generic variant, bits
+        torch.cuda.synchronize()
+        assert np.array_equal(unpack(fb), f8.cpu().numpy()) and np.array_equal(unpack(fb2), f8.cpu().numpy()), t
+        assert torch.equal(vb, v8)
+        if t % 6 == 5:                                                                           # the world model, both formats
+            cap = n * e.kmax
+            pf8 = torch.empty((cap, 2, H, W), dtype=torch.uint8, device=dev); pfb = torch.zeros((cap, 2, SW), dtype=torch.int32, device=dev)
+            pv8 = torch.empty((cap, 2, 19), dtype=torch.uint8, device=dev); pvb = torch.empty((cap, 2, 19), dtype=torch.uint8, device=dev)
+            e.expand_dev(pl, K, offs, cap, field=pf8, vec=pv8, perspective=persp)
+            e.expand_dev(pl, K, offs, cap, field=pfb, vec=pvb, perspective=persp)
+            torch.cuda.synchronize()
+            tot = int(offs[-1].item())
+            assert np.array_equal(unpack(pfb[:tot]), pf8[:tot].cpu().numpy()) and torch.equal(pv8[:tot], pvb[:tot])
+    e.close()
