@@ -57,13 +57,14 @@ class Policy:
     'sventon' (the [8]*r+[2]+[3]*t+[7] strings of agents/sventon_agent/sventon_utils.py:9-13), 'press_key' (one key per step,
     the action_type="press_key" mode: pieces come down by gravity and lock by the lockdown timer)."""
 
-    def __init__(self, kind, kmax=64, lmax=32, eps=0.05, salt=1, solo_period=0):
+    def __init__(self, kind, kmax=64, lmax=32, eps=0.05, salt=1, solo_period=0, n_players=2):
         self.kind, self.kmax, self.lmax, self.eps, self.salt, self.solo_period = kind, kmax, lmax, eps, salt, solo_period
+        self.n_players = n_players
 
     def players(self, n, t, gids):
         if self.solo_period and (t // self.solo_period) % 2 == 1:
             return np.zeros(n, np.uint8)            # same side repeatedly: exercises lockdown (SURVEY A.7-6)
-        return ((gids + t) & 1).astype(np.uint8)
+        return ((gids + t) % self.n_players).astype(np.uint8)
 
     def choose(self, lead, t, gids, player):
         n = len(gids)

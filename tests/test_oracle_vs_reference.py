@@ -109,3 +109,27 @@ print(harness.digest(np.array(out)))
 ''' % (os.path.join(harness.ROOT, "tests"), os.path.join(harness.ROOT, "oracle"))
     outs = [subprocess.check_output([sys.executable, "-c", code, var], text=True).strip() for var in ("A", "B")]
     assert outs[0] == outs[1]
+
+
+N_PLAYERS = [  # n_players, kind, H, W, games, steps: PythonHandle with 1, 3 and 4 players (PythonHandle.cpp:5-25,124-136,149-188 — the
+    (1, "random", 22, 10, 6, 200),     # float split of sent lines among the others, solo rounds that end when the one player dies)
+    (1, "greedy", 22, 10, 4, 300),
+    (3, "random", 22, 10, 6, 260),
+    (3, "greedy", 22, 10, 4, 420),
+    (3, "junk", 22, 10, 6, 200),
+    (4, "greedy", 22, 10, 3, 420),
+    (4, "press_key", 22, 10, 4, 500),
+    (3, "greedy", 16, 8, 4, 300),
+]
+
+
+@pytest.mark.parametrize("P,kind,H,W,n,steps", N_PLAYERS)
+def test_other_player_counts_match_compiled_reference(P, kind, H, W, n, steps):
+    """n_players != 2: not built in the CUDA engine, but the restatement follows the reference there too."""
+    pieces = (0, 1, 2, 3, 4, 5, 6) if W >= 10 else (0, 6)
+    lead = pyoracle.OracleVector(n, H, W, pieces, n_players=P)
+    ref = refdrive.RefVector(n, H, W, pieces, n_players=P)
+    stats = harness.rollout_pair(lead, ref, steps, harness.Policy(kind, kmax=128, lmax=64, n_players=P), compare_hidden=True)
+    assert stats["steps"] == n * steps
+    if kind == "greedy" and P > 1:
+        assert stats["lines"] > 0 and stats["garbage"] > 0, stats
