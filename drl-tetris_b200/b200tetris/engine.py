@@ -118,11 +118,11 @@ class Engine:
         placement = _np(placement, np.int32, n)
         reset_seeds = _np(reset_seeds, np.uint32, n)
         lmax = (keys.shape[1] * (2 if packed_keys else 1)) if keys is not None else 0
-        reward = np.empty(n, np.int8); done = np.empty(n, np.uint8); lines = np.empty((n, 2), np.uint8)
-        field = np.empty((n, 2, self.H, self.W), np.uint8) if want_obs else None
-        vec = np.empty((n, 2, VEC_LEN), np.uint8) if want_obs else None
-        pidx = np.empty((n, 2), np.uint8) if want_obs else None
-        scal = np.empty((n, 2, 8), np.int32) if want_scalars else None
+        reward = np.empty(n, np.int8); done = np.empty(n, np.uint8); lines = np.empty((n, self.P), np.uint8)
+        field = np.empty((n, self.P, self.H, self.W), np.uint8) if want_obs else None
+        vec = np.empty((n, self.P, VEC_LEN), np.uint8) if want_obs else None
+        pidx = np.empty((n, self.P), np.uint8) if want_obs else None
+        scal = np.empty((n, self.P, 8), np.int32) if want_scalars else None
         self._ck(self.lib.b2t_step_host(self._h, _hp(idx, C.c_int32), n, _hp(player, C.c_uint8), _hp(keys, C.c_uint8),
                                         _hp(key_len, C.c_uint8), lmax, _hp(placement, C.c_int32), int(bool(finalize)), int(time_ms),
                                         _hp(reset_seeds, C.c_uint32), _hp(reward, C.c_int8), _hp(done, C.c_uint8), _hp(lines, C.c_uint8),
@@ -137,15 +137,15 @@ class Engine:
 
     def observe(self, idx=None, want_scalars=False):
         idx, n = self._idx(idx)
-        field = np.empty((n, 2, self.H, self.W), np.uint8); vec = np.empty((n, 2, VEC_LEN), np.uint8); pidx = np.empty((n, 2), np.uint8)
-        scal = np.empty((n, 2, 8), np.int32) if want_scalars else None
+        field = np.empty((n, self.P, self.H, self.W), np.uint8); vec = np.empty((n, self.P, VEC_LEN), np.uint8); pidx = np.empty((n, self.P), np.uint8)
+        scal = np.empty((n, self.P, 8), np.int32) if want_scalars else None
         self._ck(self.lib.b2t_observe_host(self._h, _hp(idx, C.c_int32), n, _hp(field, C.c_uint8), _hp(vec, C.c_uint8),
                                            _hp(pidx, C.c_uint8), _hp(scal, C.c_int32)))
         return (field, vec, pidx, scal) if want_scalars else (field, vec, pidx)
 
     def scal(self, idx=None):
         idx, n = self._idx(idx)
-        scal = np.empty((n, 2, 8), np.int32)
+        scal = np.empty((n, self.P, 8), np.int32)
         self._ck(self.lib.b2t_observe_host(self._h, _hp(idx, C.c_int32), n, None, None, None, _hp(scal, C.c_int32)))
         return scal
 
@@ -172,12 +172,12 @@ class Engine:
             capacity = n * self.kmax
         K = np.empty(n, np.int32); offs = np.empty(n + 1, np.int32); total = C.c_int32(0)
         o = dict(keys=np.zeros((capacity, lmax), np.uint8), key_len=np.zeros(capacity, np.uint8), reward=np.zeros(capacity, np.int8),
-                 done=np.zeros(capacity, np.uint8), lines=np.zeros((capacity, 2), np.uint8))
+                 done=np.zeros(capacity, np.uint8), lines=np.zeros((capacity, self.P), np.uint8))
         if want_obs:
-            o.update(field=np.zeros((capacity, 2, self.H, self.W), np.uint8), vec=np.zeros((capacity, 2, VEC_LEN), np.uint8),
-                     piece_idx=np.zeros((capacity, 2), np.uint8))
+            o.update(field=np.zeros((capacity, self.P, self.H, self.W), np.uint8), vec=np.zeros((capacity, self.P, VEC_LEN), np.uint8),
+                     piece_idx=np.zeros((capacity, self.P), np.uint8))
         if want_scalars:
-            o["scalars"] = np.zeros((capacity, 2, 8), np.int32)
+            o["scalars"] = np.zeros((capacity, self.P, 8), np.int32)
         self._ck(self.lib.b2t_expand_host(self._h, _hp(idx, C.c_int32), n, _hp(player, C.c_uint8), int(bool(finalize)), int(time_ms), capacity,
                                           _hp(K, C.c_int32), _hp(offs, C.c_int32), C.byref(total), _hp(o["keys"], C.c_uint8),
                                           _hp(o["key_len"], C.c_uint8), lmax, _hp(o["reward"], C.c_int8), _hp(o["done"], C.c_uint8),

@@ -128,19 +128,21 @@ class tetris_environment_vector:
         s.update({k: v for k, v in (settings or {}).items() if k != "presets"})
         self.settings = s
         assert s["action_type"] in ["place_block", "press_key"]          # tetris_environment.py:205
-        assert s["n_players"] == 2, "b200tetris builds the 2-player game"
+        # the reference's own front-end runs with 2 players, and — its reward rule reading backend.states[1 - player] as a Python
+        # index — with 3 or 4 (tetris_environment.py:139); with one player that index does not exist
+        assert s["n_players"] in (2, 3, 4), "tetris_environment needs an opponent: n_players must be 2, 3 or 4"
         self.n_envs = n_envs
         self.player_idxs = list(range(s["n_players"]))
         self.envs = list(range(n_envs))
         H, W = s["game_size"]
-        self.engine = _engine_factory(n_envs, H, W, s["pieces"], 2, s["bar_null_moves"], s["time_elapsed_each_action"], device=device)
+        self.engine = _engine_factory(n_envs, H, W, s["pieces"], s["n_players"], s["bar_null_moves"], s["time_elapsed_each_action"], device=device)
         self._seed0 = int(s.get("seed", time.time()))
         self._episode = np.zeros(n_envs, np.int64)
         self.done = np.zeros(n_envs, bool)
         self.rounds_played = np.zeros(n_envs, np.int64)
-        self.round_reward = [[reward([0]), reward([0])] for _ in range(n_envs)]
-        self.tot_reward = [[reward([0]), reward([0])] for _ in range(n_envs)]
-        self._dead = np.zeros((n_envs, 2), np.uint8)
+        self.round_reward = [[reward([0]) for _ in self.player_idxs] for _ in range(n_envs)]
+        self.tot_reward = [[reward([0]) for _ in self.player_idxs] for _ in range(n_envs)]
+        self._dead = np.zeros((n_envs, s["n_players"]), np.uint8)
         self.reset()   # "Upon agreement with backend, we always reset once." tetris_environment.py:40-41
 
     # ------------------------------------------------------------------ env interface
@@ -159,7 +161,7 @@ class tetris_environment_vector:
             self._episode[i] += 1
             self.done[i] = False
             self.rounds_played[i] += 1
-            self.round_reward[i] = [reward([0]), reward([0])]
+            self.round_reward[i] = [reward([0]) for _ in self.player_idxs]
         self._dead[ids] = 0
         return [None for _ in ids]
 

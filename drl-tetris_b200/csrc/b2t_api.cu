@@ -52,6 +52,8 @@ struct Arena {  // grow-only pinned host + device scratch for the *_host calls
 struct b2t_handle {
     b2t_config cfg;
     const GeomOps* ops = nullptr;
+    int np = 2, nv = 0;             // players per game; uint4 vectors per game (ops->NV with two players)
+    bool multi() const { return np != 2; }   // served by gamen_kernel (any player count) instead of the two-player kernels
     uint4* state = nullptr;
     size_t state_vecs = 0;
     uint4* snap[B2T_SNAPSHOT_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
@@ -135,7 +137,8 @@ int b2t_create(const b2t_config* cfg, b2t_handle** out) {
     if (!cfg || !out) return fail(h, B2T_ERR_ARG, "b2t_create: NULL argument%s");
     *out = nullptr;
     if (cfg->n_games < 1) return fail(h, B2T_ERR_ARG, "b2t_create: n_games must be >= 1%s");
-    if (cfg->n_players != 2) return fail(h, B2T_ERR_UNSUPPORTED, "b2t_create: only n_players == 2 is built%s");
+    if (cfg->n_players < 1 || cfg->n_players > MAX_PLAYERS) return fail(h, B2T_ERR_UNSUPPORTED, "b2t_create: n_players must be 1..4%s");
+    if (cfg->n_players != 2 && (cfg->flags & B2T_FLAG_TILES)) return fail(h, B2T_ERR_UNSUPPORTED, "b2t_create: colour planes are built for two players only%s");
     for (int i = 0; i < 7; i++)
         if (cfg->piece_map[i] > 6) return fail(h, B2T_ERR_ARG, "b2t_create: piece_map entries must be 0..6%s");
     const GeomOps* ops = find_geom(cfg->height, cfg->width);
@@ -147,6 +150,8 @@ int b2t_create(const b2t_config* cfg, b2t_handle** out) {
     h = new b2t_handle();
     h->cfg = *cfg;
     h->ops = ops;
+    h->np = cfg->n_players;
+    h->nv = h->np == 2 ? ops->NV : (h->np * ops->PW + 3) / 4;
     if (h->cfg.time_ms_per_action <= 0) h->cfg.time_ms_per_action = 400;
     if (h->cfg.piece_stream_len <= 0) h->cfg.piece_stream_len = 4096;
     if (h->cfg.hole_stream_len <= 0) h->cfg.hole_stream_len = 512;
@@ -163,7 +168,7 @@ int b2t_create(const b2t_config* cfg, b2t_handle** out) {
     CKC(cudaSetDevice(cfg->device));
     CKC(ops->prepare());
     const size_t n = (size_t)cfg->n_games;
-    h->state_vecs = (size_t)ops->NV * 32 * ((n + 31) / 32);   // tiles of 32 games
+    h->state_vecs = (size_t)h->nv * 32 * ((n + 31) / 32);   // tiles of 32 games
     CKC(cudaMalloc((void**)&h->state, h->state_vecs * sizeof(uint4)));
     CKC(cudaMalloc((void**)&h->kcache, n * sizeof(int32_t)));
     CKC(cudaMemset(h->kcache, 0, n * sizeof(int32_t)));
@@ -171,7 +176,7 @@ int b2t_create(const b2t_config* cfg, b2t_handle** out) {
     CKC(cudaMalloc((void**)&h->d_total, 64));
     CKC(cudaMalloc((void**)&h->stats, STAT_SLICES * STAT_WORDS * sizeof(unsigned long long)));
     CKC(cudaMemset(h->stats, 0, STAT_SLICES * STAT_WORDS * sizeof(unsigned long long)));
-    CKC(cudaMalloc((void**)&h->xfer, (size_t)ops->NV * sizeof(uint4)));
+    CKC(cudaMalloc((void**)&h->xfer, (size_t)h->nv * sizeof(uint4)));
     if (cfg->flags & B2T_FLAG_TILES) {
         h->tile_words_total = (size_t)ops->tile_words * 32 * ((n + 31) / 32);
         CKC(cudaMalloc((void**)&h->tiles, h->tile_words_total * sizeof(uint32_t)));
@@ -205,7 +210,15 @@ int b2t_create(const b2t_config* cfg, b2t_handle** out) {
         fill_tables_kernel<<<RNG_SEEDS / 64, 64>>>(h->piece_tab, (uint32_t)plen, h->hole_tab, (uint32_t)hlen, pm, only_zs ? 1 : 0, cfg->width);
         CKC(cudaGetLastError());
     }
-    CKC(ops->launch_init(h->state, cfg->n_games, 0));
+    if (!h->multi()) CKC(ops->launch_init(h->state, cfg->n_games, 0));
+    else {
+        CKC(cudaMemset(h->state, 0, h->state_vecs * sizeof(uint4)));
+        KParams p;
+        memset(&p, 0, sizeof p);
+        p.state = h->state; p.n_games = cfg->n_games; p.n = cfg->n_games; p.np = h->np; p.nv = h->nv; p.tabs = h->tabs;
+        p.flags = KF_INIT | KF_STORE;
+        CKC(ops->launch_gamen(p, cfg->n_games, 0));
+    }
     CKC(cudaDeviceSynchronize());
     *out = h;
     return B2T_OK;
@@ -214,8 +227,8 @@ int b2t_create(const b2t_config* cfg, b2t_handle** out) {
 int b2t_get_info(const b2t_handle* h, b2t_info* out) {
     if (!h || !out) return B2T_ERR_ARG;
     out->kmax = h->ops->KMAX; out->lmax = h->ops->LMAX;
-    out->state_bytes = h->ops->NV * 16;
-    out->obs_bytes = 2 * (h->ops->H * h->ops->W + B2T_VEC_LEN + 1);
+    out->state_bytes = h->nv * 16;
+    out->obs_bytes = h->np * (h->ops->H * h->ops->W + B2T_VEC_LEN + 1);
     out->tile_bytes = h->tiles ? h->ops->tile_words * 4 : 0;
     return B2T_OK;
 }
@@ -224,11 +237,18 @@ static void base_params(b2t_handle* h, KParams& p) {
     memset(&p, 0, sizeof p);
     p.state = h->state; p.tiles = h->tiles; p.n_games = h->cfg.n_games; p.tabs = h->tabs; p.stats = h->stats;
     p.plc = h->plc; p.kcache = h->kcache; p.elapsed = h->cfg.time_ms_per_action;
+    p.np = h->np; p.nv = h->nv;
+}
+// the kernels of this handle's player count
+static cudaError_t launch_game(b2t_handle* h, const KParams& p, int rows, cudaStream_t s) {
+    return h->multi() ? h->ops->launch_gamen(p, rows, s) : launch_game(h, p, rows, s);
 }
 static int check_obs(b2t_handle* h, const b2t_obs& o) {
     if (!aligned16(o.d_field) || !aligned16(o.d_vec) || !aligned16(o.d_piece_idx) || !aligned16(o.d_scalars))
         return fail(h, B2T_ERR_ARG, "observation pointers must be 16-byte aligned%s");
     if (o.dtype < B2T_U8 || o.dtype > B2T_BITS) return fail(h, B2T_ERR_ARG, "b2t_obs.dtype must be B2T_U8, B2T_F16, B2T_BF16, B2T_F32 or B2T_BITS%s");
+    if (h->multi() && (o.dtype != B2T_U8 || o.perspective))
+        return fail(h, B2T_ERR_UNSUPPORTED, "n_players != 2: observations are uint8 in player-index order%s");
     return B2T_OK;
 }
 static void set_obs(KParams& p, const b2t_obs& o) {
@@ -242,7 +262,7 @@ int b2t_reset(b2t_handle* h, const int32_t* d_idx, int32_t n, const uint32_t* d_
     CK(cudaSetDevice(h->cfg.device));
     KParams p; base_params(h, p);
     p.idx = d_idx; p.n = n; p.seeds = d_seeds; p.flags = KF_RESET | KF_STORE;
-    CK(h->ops->launch_game(p, n, (cudaStream_t)stream));
+    CK(launch_game(h, p, n, (cudaStream_t)stream));
     return B2T_OK;
 }
 
@@ -254,6 +274,7 @@ static int step_launch(b2t_handle* h, const b2t_step_args* a, int32_t game0, voi
     if (!a->d_placement && (!a->d_keys || a->lmax < 1)) return fail(h, B2T_ERR_ARG, "b2t_step: need d_placement or d_keys+lmax%s");
     if (a->key_format != B2T_KEYS_U8 && a->key_format != B2T_KEYS_PACKED4) return fail(h, B2T_ERR_ARG, "b2t_step: bad key_format%s");
     if (a->key_format == B2T_KEYS_PACKED4 && (a->lmax & 7)) return fail(h, B2T_ERR_ARG, "b2t_step: packed keys need lmax to be a multiple of 8%s");
+    if (h->multi() && a->key_format != B2T_KEYS_U8) return fail(h, B2T_ERR_UNSUPPORTED, "n_players != 2: keys are one code per byte%s");
     if (a->d_placement && !h->enumerated) return fail(h, B2T_ERR_STATE, "b2t_step: d_placement needs a prior b2t_enumerate/b2t_expand%s");
     if (int r = check_obs(h, a->obs)) return r;
     CK(cudaSetDevice(h->cfg.device));
@@ -266,7 +287,7 @@ static int step_launch(b2t_handle* h, const b2t_step_args* a, int32_t game0, voi
     p.reset_seeds = a->d_reset_seeds;
     p.reward = a->d_reward; p.done = a->d_done; p.lines = a->d_lines;
     set_obs(p, a->obs);
-    CK(h->ops->launch_game(p, a->n, (cudaStream_t)stream));
+    CK(launch_game(h, p, a->n, (cudaStream_t)stream));
     return B2T_OK;
 }
 
@@ -279,7 +300,7 @@ int b2t_observe(b2t_handle* h, const int32_t* d_idx, int32_t n, const b2t_obs* o
     KParams p; base_params(h, p);
     p.idx = d_idx; p.n = n; p.flags = 0;
     set_obs(p, *obs);
-    CK(h->ops->launch_game(p, n, (cudaStream_t)stream));
+    CK(launch_game(h, p, n, (cudaStream_t)stream));
     return B2T_OK;
 }
 
@@ -299,6 +320,7 @@ int b2t_enumerate(b2t_handle* h, const int32_t* d_idx, int32_t n, const uint8_t*
     EParams e;
     memset(&e, 0, sizeof e);
     e.state = h->state; e.n_games = h->cfg.n_games; e.idx = d_idx; e.n = n; e.player = d_player;
+    e.nv = h->nv; e.np = h->np;
     e.bar_null = h->cfg.bar_null_moves ? 1 : 0; e.plc = h->plc; e.kcache = h->kcache; e.K = d_K; e.stats = h->stats; e.tabs = h->tabs;
     CK(h->ops->launch_enum(e, (cudaStream_t)stream));
     h->enumerated = true;
@@ -340,7 +362,7 @@ int b2t_expand(b2t_handle* h, const b2t_expand_args* a, void* stream) {
     p.reward = a->d_reward; p.done = a->d_done; p.lines = a->d_lines;
     p.keys_out = a->d_keys; p.key_len_out = a->d_key_len; p.lmax_out = a->lmax;
     set_obs(p, a->obs);
-    CK(h->ops->launch_game(p, a->capacity, s));
+    CK(launch_game(h, p, a->capacity, s));
     return B2T_OK;
 }
 
@@ -375,9 +397,9 @@ int b2t_export_state(b2t_handle* h, int32_t game, void* h_buf, void* stream) {
     if (!h || !h_buf || game < 0 || game >= h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_export_state: bad argument%s");
     CK(cudaSetDevice(h->cfg.device));
     cudaStream_t s = (cudaStream_t)stream;
-    gather_game_kernel<<<1, 64, 0, s>>>(h->state, game, h->ops->NV, h->xfer);
+    gather_game_kernel<<<(h->nv + 63) / 64, 64, 0, s>>>(h->state, game, h->nv, h->xfer);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(h_buf, h->xfer, (size_t)h->ops->NV * 16, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h_buf, h->xfer, (size_t)h->nv * 16, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return B2T_OK;
 }
@@ -385,8 +407,8 @@ int b2t_import_state(b2t_handle* h, int32_t game, const void* h_buf, void* strea
     if (!h || !h_buf || game < 0 || game >= h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_import_state: bad argument%s");
     CK(cudaSetDevice(h->cfg.device));
     cudaStream_t s = (cudaStream_t)stream;
-    CK(cudaMemcpyAsync(h->xfer, h_buf, (size_t)h->ops->NV * 16, cudaMemcpyHostToDevice, s));
-    scatter_game_kernel<<<1, 64, 0, s>>>(h->state, game, h->ops->NV, h->xfer);
+    CK(cudaMemcpyAsync(h->xfer, h_buf, (size_t)h->nv * 16, cudaMemcpyHostToDevice, s));
+    scatter_game_kernel<<<(h->nv + 63) / 64, 64, 0, s>>>(h->state, game, h->nv, h->xfer);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
     return B2T_OK;
@@ -401,6 +423,7 @@ static int fetch_tiles(b2t_handle* h, int32_t game, std::vector<uint32_t>& plane
 }
 int b2t_get_game(b2t_handle* h, int32_t game, b2t_game_raw* out, uint8_t* h_field) {
     if (!h || !out || game < 0 || game >= h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_get_game: bad argument%s");
+    if (h->multi()) return fail(h, B2T_ERR_UNSUPPORTED, "b2t_get_game: b2t_game_raw describes two players%s");
     std::vector<uint32_t> words((size_t)h->ops->NV * 4), planes;
     if (int r = b2t_export_state(h, game, words.data(), nullptr)) return r;
     if (h->tiles && h_field)
@@ -410,6 +433,7 @@ int b2t_get_game(b2t_handle* h, int32_t game, b2t_game_raw* out, uint8_t* h_fiel
 }
 int b2t_set_game(b2t_handle* h, int32_t game, const b2t_game_raw* in, const uint8_t* h_field) {
     if (!h || !in || game < 0 || game >= h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_set_game: bad argument%s");
+    if (h->multi()) return fail(h, B2T_ERR_UNSUPPORTED, "b2t_set_game: b2t_game_raw describes two players%s");
     for (int p = 0; p < 2; p++)
         if (in->player[p].piece_kind < 0 || in->player[p].piece_kind > 7 || in->player[p].nextpiece < 0 || in->player[p].nextpiece > 7)
             return fail(h, B2T_ERR_ARG, "b2t_set_game: piece_kind / nextpiece out of range%s");
@@ -428,10 +452,10 @@ int b2t_copy_game(b2t_handle* to, int32_t dst, b2t_handle* from, int32_t src, vo
     b2t_handle* h = to;
     if (!to || !from || dst < 0 || dst >= to->cfg.n_games || src < 0 || src >= from->cfg.n_games)
         return fail(h, B2T_ERR_ARG, "b2t_copy_game: bad argument%s");
-    if (to->ops != from->ops || to->cfg.device != from->cfg.device)
-        return fail(h, B2T_ERR_ARG, "b2t_copy_game: handles differ in field size or device%s");
+    if (to->ops != from->ops || to->cfg.device != from->cfg.device || to->np != from->np)
+        return fail(h, B2T_ERR_ARG, "b2t_copy_game: handles differ in field size, player count or device%s");
     CK(cudaSetDevice(h->cfg.device));
-    copy_game_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(to->state, dst, from->state, src, h->ops->NV);
+    copy_game_kernel<<<(h->nv + 63) / 64, 64, 0, (cudaStream_t)stream>>>(to->state, dst, from->state, src, h->nv);
     if (to->tiles)   // colours travel with the game (a source without planes reads as all ones)
         copy_tiles_kernel<<<(h->ops->tile_words + 63) / 64, 64, 0, (cudaStream_t)stream>>>(to->tiles, dst, from->tiles, src, h->ops->tile_words);
     CK(cudaGetLastError());
@@ -439,14 +463,14 @@ int b2t_copy_game(b2t_handle* to, int32_t dst, b2t_handle* from, int32_t src, vo
 }
 
 static int poke(b2t_handle* h, int32_t game, int32_t player, uint32_t flag, int value, void* stream) {
-    if (!h || game < 0 || game >= h->cfg.n_games || player < 0 || player > 1) return fail(h, B2T_ERR_ARG, "poke: bad game/player%s");
+    if (!h || game < 0 || game >= h->cfg.n_games || player < 0 || player >= h->np) return fail(h, B2T_ERR_ARG, "poke: bad game/player%s");
     CK(cudaSetDevice(h->cfg.device));
     cudaStream_t s = (cudaStream_t)stream;
     int32_t* d_idx = reinterpret_cast<int32_t*>(h->d_total) + 4;
     CK(cudaMemcpyAsync(d_idx, &game, sizeof game, cudaMemcpyHostToDevice, s));
     KParams p; base_params(h, p);
     p.idx = d_idx; p.n = 1; p.flags = flag | KF_STORE; p.poke_player = player; p.poke_value = value;
-    CK(h->ops->launch_game(p, 1, s));
+    CK(launch_game(h, p, 1, s));
     CK(cudaStreamSynchronize(s));
     return B2T_OK;
 }
@@ -559,13 +583,13 @@ int b2t_export_states(b2t_handle* h, const int32_t* h_idx, int32_t n, void* h_bu
     if (!n) return B2T_OK;
     CK_IDS("b2t_export_states");
     CK(cudaSetDevice(h->cfg.device));
-    const size_t bytes = (size_t)n * h->ops->NV * 16;
+    const size_t bytes = (size_t)n * h->nv * 16;
     In idx; idx.src = h_idx; idx.bytes = (size_t)n * 4;
     if (int r = stage_in(h, {&idx}, 0)) return r;
     Out buf; buf.dst = h_buf; buf.bytes = bytes;
     if (int r = plan_out(h, {&buf})) return r;
-    const long long t = (long long)n * h->ops->NV;
-    gather_games_kernel<<<(unsigned)((t + 255) / 256), 256>>>(h->state, h->cfg.n_games, (const int32_t*)dev_in(h->in, idx), n, h->ops->NV, (uint4*)dev_out(h->out, buf));
+    const long long t = (long long)n * h->nv;
+    gather_games_kernel<<<(unsigned)((t + 255) / 256), 256>>>(h->state, h->cfg.n_games, (const int32_t*)dev_in(h->in, idx), n, h->nv, (uint4*)dev_out(h->out, buf));
     CK(cudaGetLastError());
     return fetch_out(h, {&buf}, 0);
 }
@@ -574,10 +598,10 @@ int b2t_import_states(b2t_handle* h, const int32_t* h_idx, int32_t n, const void
     if (!n) return B2T_OK;
     CK_IDS("b2t_import_states");
     CK(cudaSetDevice(h->cfg.device));
-    In idx, buf; idx.src = h_idx; idx.bytes = (size_t)n * 4; buf.src = h_buf; buf.bytes = (size_t)n * h->ops->NV * 16;
+    In idx, buf; idx.src = h_idx; idx.bytes = (size_t)n * 4; buf.src = h_buf; buf.bytes = (size_t)n * h->nv * 16;
     if (int r = stage_in(h, {&idx, &buf}, 0)) return r;
-    const long long t = (long long)n * h->ops->NV;
-    scatter_games_kernel<<<(unsigned)((t + 255) / 256), 256>>>(h->state, h->cfg.n_games, (const int32_t*)dev_in(h->in, idx), n, h->ops->NV, (const uint4*)dev_in(h->in, buf));
+    const long long t = (long long)n * h->nv;
+    scatter_games_kernel<<<(unsigned)((t + 255) / 256), 256>>>(h->state, h->cfg.n_games, (const int32_t*)dev_in(h->in, idx), n, h->nv, (const uint4*)dev_in(h->in, buf));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(0));
     return B2T_OK;
@@ -604,16 +628,16 @@ int b2t_step_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint8_t*
     if (n < 0 || n > h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_step_host: bad n%s");
     CK_IDS("b2t_step_host");
     CK(cudaSetDevice(h->cfg.device));
-    const size_t N = (size_t)n, HW = (size_t)h->ops->H * h->ops->W;
+    const size_t N = (size_t)n, HW = (size_t)h->ops->H * h->ops->W, P = (size_t)h->np;
     In idx, pl, keys, klen, plc, rs;
     idx.src = h_idx; idx.bytes = N * 4; pl.src = h_player; pl.bytes = N;
     const size_t key_row = (size_t)(lmax > 0 ? lmax : 0) >> (key_format == B2T_KEYS_PACKED4 ? 1 : 0);
     keys.src = h_keys; keys.bytes = N * key_row; klen.src = h_key_len; klen.bytes = N;
     plc.src = h_placement; plc.bytes = N * 4; rs.src = h_reset_seeds; rs.bytes = N * 4;
     Out rew, done, lines, field, vec, pidx, scal;
-    rew.dst = h_reward; rew.bytes = N; done.dst = h_done; done.bytes = N; lines.dst = h_lines; lines.bytes = 2 * N;
-    field.dst = h_field; field.bytes = 2 * HW * N; vec.dst = h_vec; vec.bytes = 2 * B2T_VEC_LEN * N;
-    pidx.dst = h_piece_idx; pidx.bytes = 2 * N; scal.dst = h_scalars; scal.bytes = 64 * N;
+    rew.dst = h_reward; rew.bytes = N; done.dst = h_done; done.bytes = N; lines.dst = h_lines; lines.bytes = P * N;
+    field.dst = h_field; field.bytes = P * HW * N; vec.dst = h_vec; vec.bytes = P * B2T_VEC_LEN * N;
+    pidx.dst = h_piece_idx; pidx.bytes = P * N; scal.dst = h_scalars; scal.bytes = 32 * P * N;
     {
         // Large batch, every buffer pinned, no observation tensors asked for: the kernel reads the keys and writes reward / done /
         // lines straight through the caller's pinned pages (they are device-addressable under unified addressing), so the
@@ -656,7 +680,7 @@ int b2t_step_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint8_t*
         std::vector<In*> ins = {&idx, &pl, &keys, &klen, &plc, &rs};
         std::vector<Out*> outs = {&rew, &done, &lines, &field, &vec, &pidx, &scal};
         const size_t in_row[6] = {4, 1, key_row, 1, 4, 4};
-        const size_t out_row[7] = {1, 1, 2, 2 * HW, 2 * B2T_VEC_LEN, 2, 64};
+        const size_t out_row[7] = {1, 1, P, P * HW, P * B2T_VEC_LEN, P, 32 * P};
         size_t total = 0;
         for (auto i : ins) if (i->src) total += (i->bytes + 255) & ~(size_t)255;
         CK(h->in.reserve(total + 256));
@@ -709,9 +733,9 @@ int b2t_step_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint8_t*
         return B2T_OK;
     }
     if (int r = stage_in(h, {&idx, &pl, &keys, &klen, &plc, &rs}, 0)) return r;
-    rew.dst = h_reward; rew.bytes = N; done.dst = h_done; done.bytes = N; lines.dst = h_lines; lines.bytes = 2 * N;
-    field.dst = h_field; field.bytes = 2 * HW * N; vec.dst = h_vec; vec.bytes = 2 * B2T_VEC_LEN * N;
-    pidx.dst = h_piece_idx; pidx.bytes = 2 * N; scal.dst = h_scalars; scal.bytes = 64 * N;
+    rew.dst = h_reward; rew.bytes = N; done.dst = h_done; done.bytes = N; lines.dst = h_lines; lines.bytes = P * N;
+    field.dst = h_field; field.bytes = P * HW * N; vec.dst = h_vec; vec.bytes = P * B2T_VEC_LEN * N;
+    pidx.dst = h_piece_idx; pidx.bytes = P * N; scal.dst = h_scalars; scal.bytes = 32 * P * N;
     if (int r = plan_out(h, {&rew, &done, &lines, &field, &vec, &pidx, &scal})) return r;
     b2t_step_args a;
     memset(&a, 0, sizeof a);
@@ -731,12 +755,12 @@ int b2t_observe_host(b2t_handle* h, const int32_t* h_idx, int32_t n, uint8_t* h_
     if (n < 0 || n > h->cfg.n_games) return fail(h, B2T_ERR_ARG, "b2t_observe_host: bad n%s");
     CK_IDS("b2t_observe_host");
     CK(cudaSetDevice(h->cfg.device));
-    const size_t N = (size_t)n, HW = (size_t)h->ops->H * h->ops->W;
+    const size_t N = (size_t)n, HW = (size_t)h->ops->H * h->ops->W, P = (size_t)h->np;
     In idx; idx.src = h_idx; idx.bytes = N * 4;
     if (int r = stage_in(h, {&idx}, 0)) return r;
     Out field, vec, pidx, scal;
-    field.dst = h_field; field.bytes = 2 * HW * N; vec.dst = h_vec; vec.bytes = 2 * B2T_VEC_LEN * N;
-    pidx.dst = h_piece_idx; pidx.bytes = 2 * N; scal.dst = h_scalars; scal.bytes = 64 * N;
+    field.dst = h_field; field.bytes = P * HW * N; vec.dst = h_vec; vec.bytes = P * B2T_VEC_LEN * N;
+    pidx.dst = h_piece_idx; pidx.bytes = P * N; scal.dst = h_scalars; scal.bytes = 32 * P * N;
     if (int r = plan_out(h, {&field, &vec, &pidx, &scal})) return r;
     b2t_obs o;
     memset(&o, 0, sizeof o);
@@ -771,7 +795,7 @@ int b2t_expand_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint8_
     if (n < 1 || n > h->cfg.n_games || !h_player || capacity < 0) return fail(h, B2T_ERR_ARG, "b2t_expand_host: bad n/capacity or NULL player%s");
     CK_IDS("b2t_expand_host");
     CK(cudaSetDevice(h->cfg.device));
-    const size_t N = (size_t)n, C = (size_t)capacity, HW = (size_t)h->ops->H * h->ops->W;
+    const size_t N = (size_t)n, C = (size_t)capacity, HW = (size_t)h->ops->H * h->ops->W, P = (size_t)h->np;
     In idx, pl; idx.src = h_idx; idx.bytes = N * 4; pl.src = h_player; pl.bytes = N;
     if (int r = stage_in(h, {&idx, &pl}, 0)) return r;
     Out K, offs, keys, klen, rew, done, lines, field, vec, pidx, scal;
@@ -780,9 +804,9 @@ int b2t_expand_host(b2t_handle* h, const int32_t* h_idx, int32_t n, const uint8_
     if (!h_offsets) { o_tmp.resize(N + 1); h_offsets = o_tmp.data(); }
     K.dst = h_K; K.bytes = N * 4; offs.dst = h_offsets; offs.bytes = (N + 1) * 4;
     keys.dst = h_keys; keys.bytes = C * (size_t)(lmax > 0 ? lmax : 0); klen.dst = h_key_len; klen.bytes = C;
-    rew.dst = h_reward; rew.bytes = C; done.dst = h_done; done.bytes = C; lines.dst = h_lines; lines.bytes = 2 * C;
-    field.dst = h_field; field.bytes = 2 * HW * C; vec.dst = h_vec; vec.bytes = 2 * B2T_VEC_LEN * C; pidx.dst = h_piece_idx; pidx.bytes = 2 * C;
-    scal.dst = h_scalars; scal.bytes = 64 * C;
+    rew.dst = h_reward; rew.bytes = C; done.dst = h_done; done.bytes = C; lines.dst = h_lines; lines.bytes = P * C;
+    field.dst = h_field; field.bytes = P * HW * C; vec.dst = h_vec; vec.bytes = P * B2T_VEC_LEN * C; pidx.dst = h_piece_idx; pidx.bytes = P * C;
+    scal.dst = h_scalars; scal.bytes = 32 * P * C;
     if (int r = plan_out(h, {&K, &offs, &keys, &klen, &rew, &done, &lines, &field, &vec, &pidx, &scal})) return r;
     b2t_expand_args a;
     memset(&a, 0, sizeof a);

@@ -799,6 +799,90 @@ B2T_HD void reset_game(PS& p0, const Board<G, S>& b0, PS& p1, const Board<G, S>&
     gf = ((winner + 1) << GF_WINNER_SHIFT);
 }
 
+// ------------------------------------------------------------------------------------------------ any number of players
+// The two-player game above is what every BASELINE configuration and every preset of the reference runs, and what the fast
+// kernels are built for.  PythonHandle itself takes any player count (PythonHandle.cpp:5-25): with one player a round ends when
+// that player dies (check_for_winner stays false), with three or more the lines a player sends are split evenly — as a float —
+// among ALL the others, dead or alive (distributeLines :124-136), and the fraction a player has not yet received as a whole line
+// stays in GamePlay::incoming_lines (gamePlay.cpp:97-102).  These routines restate that for 1..MAX_PLAYERS players; the kernels
+// that use them (gamen_kernel) keep the scalars of all players in local memory and are the compatibility path for n_players != 2.
+constexpr int MAX_PLAYERS = 4;
+B2T_HD float f_sub(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fsub_rn(a, b);
+#else
+    volatile float r = a - b; return r;
+#endif
+}
+// gamePlay.cpp:90-114 delayCheck with the float incoming_lines of the reference: -1 = died, else lines sent
+template <class G, int S> B2T_HD int delay_check_f(PS& s, float& incoming, const Board<G, S>& b, const Tabs& tb, uint32_t seed16, int elapsed) {
+    s.time_ms += elapsed;
+    if (dd_check(s, s.time_ms)) gp_move_down<G, S>(s, b, tb);
+    if (s.lockdown && s.time_ms > s.lockdown_time && !gp_move_down<G, S>(s, b, tb)) {  // DropDelay.cpp:43-48
+        hd_make<G, S>(s, b, tb);
+        return hd_finish<G, S>(s, b, tb, seed16);
+    }
+    int add = 0;
+    while (incoming >= 1.f) { add++; incoming = f_sub(incoming, 1.f); }                  // :97-101
+    if (add) gq_add<S>(s, add, s.time_ms);
+    int sent = cb_check(s, s.time_ms, tb);
+    if (sent) sent = gq_block<S>(s, sent, s.time_ms, false);
+    if (gq_check<S>(s, s.time_ms))
+        if (push_garbage<G, S>(s, b, tb, seed16)) return -1;
+    return sent;
+}
+// PythonHandle.cpp:124-136 distributeLines
+B2T_HD void distribute_lines(float* incoming, int np, int sender, int amount) {
+    const float others = (float)(np - 1);
+    if (others < 1.f) return;
+    const float each = f_div((float)amount, others);
+    for (int i = 0; i < np; i++)
+        if (i != sender) incoming[i] = f_add(incoming[i], each);
+}
+// PythonHandle.cpp:149-188 finish_actions for np players; returns round_over
+template <class G, int S>
+B2T_HD bool finish_actions_n(PS* p, const Board<G, S>* b, float* incoming, int np, const Tabs& tb, uint32_t seed16, int elapsed, int& gf) {
+    if (gf & GF_ROUND_OVER) return true;
+    for (int i = 0; i < np; i++) {                     // phase A (:151-158): a death ends it for everyone after
+        if (p[i].dead) continue;
+        const int sent = hd_finish<G, S>(p[i], b[i], tb, seed16);
+        if (sent == -1) { p[i].dead = 1; break; }
+        if (sent) distribute_lines(incoming, np, i, sent);
+    }
+    int alive = 0;
+    for (int i = 0; i < np; i++) {                     // phase B (:160-180)
+        if (p[i].dead) continue;
+        const int sent = delay_check_f<G, S>(p[i], incoming[i], b[i], tb, seed16, elapsed);
+        if (sent == -1) { p[i].dead = 1; continue; }
+        if (sent) distribute_lines(incoming, np, i, sent);
+        alive++;
+        p[i].reward = p[i].pending & 255; p[i].pending = 0;
+        p[i].inc_count = gq_total<S>(p[i]) & 255;
+    }
+    if ((np > 1 && alive < 2) || !alive) { gf |= GF_ROUND_OVER; return true; }   // check_for_winner = n_players > 1 (:13)
+    return false;
+}
+// PythonHandle.cpp:49-66 reset for np players (last_winner: the last alive player in index order, -1 if several are alive or none;
+// `if (!player_count) last_winner = 0` makes it 0 for a single player)
+template <class G, int S>
+B2T_HD void reset_game_n(PS* p, const Board<G, S>* b, float* incoming, int np, const Tabs& tb, uint32_t seed16, int& gf) {
+    int winner = -1, alive = 0;
+    for (int i = 0; i < np; i++) {
+        if (!p[i].dead) { alive++; winner = i; }
+        restart_and_seed<G, S>(p[i], b[i], tb, seed16);
+        incoming[i] = 0.f;
+    }
+    if (np == 1) winner = 0;
+    if (alive > 1) winner = -1;
+    gf = (((winner + 1) & 3) << GF_WINNER_SHIFT);   // (two bits: not observable through the n-player entry points)
+}
+// tetris_environment.py:135-149 reward_fcn reads backend.states[1 - player]: a Python index, so for players beyond the second it
+// counts from the end of the list (player 2 of 3 reads itself)
+B2T_HD int opponent_index(int player, int np) {
+    const int i = 1 - player;
+    return i >= 0 ? i : np + i;
+}
+
 // Engine-chosen seed of a round (b2t_step_args.auto_reset): what time(NULL) is to the reference (PythonHandle.cpp:68-71) — any
 // value will do, only its low 16 bits matter — as a counter hash of (handle seed, game id, rounds started), so a run is
 // reproducible and independent of how games are batched or sharded.

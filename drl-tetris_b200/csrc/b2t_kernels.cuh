@@ -40,7 +40,8 @@ enum : uint32_t {
     KF_STORE = 8u,      // write the state back
     KF_EXPAND = 16u,    // rows are placements (offsets/placement cache), never stores
     KF_POKE_DEAD = 32u, // state.lock()-style write: p.poke_player / p.poke_value
-    KF_CLEAR_FIELD = 64u
+    KF_CLEAR_FIELD = 64u,
+    KF_INIT = 128u      // gamen_kernel: a never-reset game instead of the stored one (b2t_create)
 };
 
 struct KParams {
@@ -84,6 +85,7 @@ struct KParams {
     uint8_t* key_len_out;
     int32_t lmax_out;
     unsigned long long* stats;    // [STAT_SLICES][STAT_WORDS]
+    int32_t np, nv;               // players per game and uint4 vectors per game (gamen_kernel; the two-player kernels know both at compile time)
     DevTabs tabs;
 };
 
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(TPB, MODE == GM_EXPAND ? B2T_GAME_MINB + 1 : B
     if (active) {
         if (expand) {
             const int4 m = p.row_meta[row];
-            i = m.x; gi = m.y; k = m.z; player = m.w; sel = k;
+            i = m.x; gi = m.y; k = m.z; player = m.w ? 1 : 0; sel = k;
         } else gi = p.idx ? p.idx[i] : i + p.game0;
         // a game id outside the handle (the caller's list is never trusted with the state array, the placement cache or kcache):
         // the row is inert — nothing is read or written for it and its observation rows come out as zeros
@@ -648,6 +650,7 @@ struct EParams {
     int32_t* kcache;    // [n_games]
     int32_t* K;         // [n] (may be NULL)
     unsigned long long* stats;
+    int32_t nv, np;     // uint4 vectors per game (G::NV with two players), players per game
     DevTabs tabs;
 };
 
@@ -762,9 +765,10 @@ __global__ void __launch_bounds__(ETPB, EMINB) enumerate_kernel(const EParams p)
         }
     }
     if (active) {
-        const int pl = p.player[i] ? 1 : 0;
+        const int pl = p.player[i] < p.np ? p.player[i] : p.np - 1;
         const uint32_t* words = reinterpret_cast<const uint32_t*>(p.state);
-        auto word = [&](int wi) { return words[state_index<G>(gi, wi >> 2) * 4 + (wi & 3)]; };
+        const size_t tile = (size_t)(gi >> 5) * (size_t)p.nv;      // (nv is G::NV unless the handle has another player count)
+        auto word = [&](int wi) { return words[((tile + (size_t)(wi >> 2)) * 32 + (size_t)(gi & 31)) * 4 + (wi & 3)]; };
         const int base = pl * G::PW;
         for (int c = 0; c < G::W; c++) {
             if (G::CW == 1) b.col(c) = (col_t)word(base + c);
@@ -1070,7 +1074,7 @@ __global__ void __launch_bounds__(256) fill_row_meta(const int32_t* offsets, int
     const int b0 = blockIdx.x * 256, tid = threadIdx.x;
     const int nb = (n - b0) < 256 ? (n - b0) : 256;
     for (int t = tid; t <= nb; t += 256) s_off[t] = offsets[b0 + t];
-    if (tid < nb) { s_gi[tid] = idx ? idx[b0 + tid] : b0 + tid; s_pl[tid] = player[b0 + tid] ? 1 : 0; }
+    if (tid < nb) { s_gi[tid] = idx ? idx[b0 + tid] : b0 + tid; s_pl[tid] = player[b0 + tid]; }   // (the kernels clamp the player index)
     __syncthreads();
     const int r0 = s_off[0];
     int r1 = s_off[nb];
@@ -1180,6 +1184,208 @@ __global__ void copy_game_kernel(uint4* dst_state, int dst, const uint4* src_sta
 
 #endif  // B2T_COMMON_KERNELS
 
+// ---------------------------------------------------------------------------------------------- any number of players
+// n_players != 2 (PythonHandle takes any count, PythonHandle.cpp:5-25; no BASELINE configuration or preset of the reference uses
+// one): the same rules (b2t_core.cuh: finish_actions_n and friends) run by a plain kernel — one thread per game or simulated
+// placement, every player's board in shared memory, every player's scalars in local memory, byte-wise outputs.  It serves reset,
+// step (keys or placement index, fused reset), observe, expand and the pokes for handles created with 1, 3 or 4 players; the
+// enumerate kernel is shared.  HBM layout: the tile-of-32 layout with nv = ceil(np*PW/4) vectors per game; a player's 24th
+// scalar word holds the float GamePlay::incoming_lines, the spare bits 26..29 of player 0's first scalar word the game flags.
+constexpr int NTPB = 64;
+template <class G> struct SmemLayoutN {
+    static constexpr int PER_PLAYER = G::NCOL * (int)sizeof(typename G::col_t) + (G::SW + GQ_WORDS) * 4;   // bytes per thread
+    static constexpr int total(int np) { return np * PER_PLAYER * NTPB + 128; }
+};
+
+template <class G>
+__global__ void __launch_bounds__(NTPB) gamen_kernel(const KParams p) {
+    typedef typename G::col_t col_t;
+    constexpr int KW = G::KEYW, W0 = G::W * G::CW, SCAL0 = W0 + G::SW;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, np = p.np;
+    uint16_t* s_tab = reinterpret_cast<uint16_t*>(smem);
+    col_t* s_cols = reinterpret_cast<col_t*>(smem + 128);
+    uint32_t* s_stream = reinterpret_cast<uint32_t*>(smem + 128 + (size_t)np * G::NCOL * NTPB * sizeof(col_t));
+    uint32_t* s_gq = s_stream + (size_t)np * G::SW * NTPB;
+    if (tid < 28) { s_tab[tid] = p.tabs.pcn[tid]; s_tab[32 + tid] = p.tabs.pcc[tid]; }
+    Tabs tb;
+    tb.pcn = s_tab; tb.pcc = s_tab + 32;
+    tb.piece = p.tabs.piece; tb.hole = p.tabs.hole; tb.powtab = p.tabs.powtab;
+    tb.piece_len = p.tabs.piece_len; tb.hole_len = p.tabs.hole_len; tb.spawn_rots = p.tabs.spawn_rots;
+    PS ps[MAX_PLAYERS];
+    Board<G, NTPB> bd[MAX_PLAYERS];
+    float inc[MAX_PLAYERS];
+    for (int pl = 0; pl < np; pl++) {
+        bd[pl].cols = s_cols + (size_t)pl * G::NCOL * NTPB + tid;
+        bd[pl].stream = s_stream + (size_t)pl * G::SW * NTPB + tid;
+        ps[pl].gq = s_gq + (size_t)pl * GQ_WORDS * NTPB + tid;
+        board_init_walls<G, NTPB>(bd[pl]);
+        inc[pl] = 0.f;
+    }
+    __syncthreads();
+    const uint32_t flags = p.flags;
+    const bool expand = (flags & KF_EXPAND) != 0, stepping = (flags & (KF_STEP | KF_EXPAND)) != 0;
+    const int row = blockIdx.x * NTPB + tid;
+    int total_rows = p.n, i = row, player = 0, sel = 0, gi = 0;
+    if (expand) {
+        total_rows = p.offsets[p.n];
+        if (total_rows > p.capacity) total_rows = p.capacity;
+    }
+    if (row >= total_rows) return;
+    if (expand) {
+        const int4 m = p.row_meta[row];
+        i = m.x; gi = m.y; sel = m.z; player = m.w;
+    } else gi = p.idx ? p.idx[i] : i + p.game0;
+    if ((unsigned)gi >= (unsigned)p.n_games) return;       // a foreign id: an inert row
+    uint32_t* words = reinterpret_cast<uint32_t*>(p.state);
+    const size_t tile = (size_t)(gi >> 5) * (size_t)p.nv;
+    auto widx = [&](int wi) { return ((tile + (size_t)(wi >> 2)) * 32 + (size_t)(gi & 31)) * 4 + (size_t)(wi & 3); };
+    int gf = 0;
+    if (flags & KF_INIT) {
+        for (int pl = 0; pl < np; pl++) {
+            board_clear<G, NTPB>(bd[pl]);
+            uint32_t z[14];
+            for (int k = 0; k < 14; k++) z[k] = 0u;
+            ps_unpack(ps[pl], z);
+            for (int j = 0; j < GQ_WORDS; j++) ps[pl].gq[j * NTPB] = 0u;
+            ps[pl].kind = 7; ps[pl].min_remaining = 1000; ps[pl].drop_delay = 1000;
+        }
+    } else {
+        for (int pl = 0; pl < np; pl++) {
+            const int base = pl * G::PW;
+            for (int c = 0; c < G::W; c++) {
+                if (G::CW == 1) bd[pl].col(c) = (col_t)words[widx(base + c)];
+                else bd[pl].col(c) = (col_t)((uint64_t)words[widx(base + 2 * c)] | ((uint64_t)words[widx(base + 2 * c + 1)] << 32));
+            }
+            for (int j = 0; j < G::SW; j++) bd[pl].sw(j) = words[widx(base + W0 + j)];
+            uint32_t sc[14];
+            for (int k = 0; k < 14; k++) sc[k] = words[widx(base + SCAL0 + k)];
+            if (pl == 0) { gf = (int)(sc[0] >> 26) & 15; sc[0] &= 0x03FFFFFFu; }
+            ps_unpack(ps[pl], sc);
+            for (int j = 0; j < GQ_WORDS; j++) ps[pl].gq[j * NTPB] = words[widx(base + SCAL0 + 14 + j)];
+            inc[pl] = __uint_as_float(words[widx(base + SCAL0 + 23)]);
+        }
+    }
+    uint32_t seed16 = ps[0].hi12 & 0xFFFFu;
+    int flags_before = 0;
+    for (int pl = 0; pl < np; pl++) flags_before |= ps[pl].flags;
+    auto do_reset = [&](uint32_t seed) {
+        seed16 = seed & 0xFFFFu;
+        reset_game_n<G, NTPB>(ps, bd, inc, np, tb, seed16, gf);
+        ps[0].episode = (ps[0].episode + 1u) & 0xFFFFu;
+        ps[0].hi12 = seed16;
+    };
+    if (flags & KF_RESET) do_reset(p.seeds[i]);
+    if ((flags & KF_POKE_DEAD) && p.poke_player >= 0 && p.poke_player < np) ps[p.poke_player].dead = p.poke_value;
+    if ((flags & KF_CLEAR_FIELD) && p.poke_player >= 0 && p.poke_player < np) board_clear<G, NTPB>(bd[p.poke_player]);
+    if (stepping) {
+        if (!expand) {
+            player = p.player[i];
+            if (p.placement) sel = p.placement[i];
+        }
+        if (player >= np) player = np - 1;
+        uint32_t kw[KW];
+        int nkeys = 1;
+        if (expand || p.placement) {
+            const int kc = p.kcache[gi];
+            const bool valid = sel >= 0 && sel < kc && sel < G::KMAX;   // out of range -> null action (action_list.py:27-33)
+            const uint32_t* src = p.plc + ((size_t)gi * G::KMAX + (valid ? sel : 0)) * KW;
+            for (int j = 0; j < KW; j++) kw[j] = valid ? src[j] : 0u;
+            nkeys = packed_len<KW>(kw);
+        } else {
+            const bool zterm = p.key_len == nullptr;
+            nkeys = zterm ? KW * 8 : (int)p.key_len[i];
+            if (nkeys > KW * 8) nkeys = KW * 8;
+            if (nkeys > p.lmax) nkeys = p.lmax;
+            const uint8_t* kp = p.keys + (size_t)i * (size_t)p.lmax;
+            for (int j = 0; j < KW; j++) {
+                uint32_t w = 0;
+                for (int b = 0; b < 8; b++) {
+                    const int at = 8 * j + b;
+                    if (at < nkeys) { const uint32_t k = kp[at]; w |= (k <= 10u ? k : 0u) << (4 * b); }
+                }
+                kw[j] = w;
+            }
+            if (zterm) { nkeys = packed_len<KW>(kw); if (nkeys > p.lmax) nkeys = p.lmax; }
+        }
+        const bool was_over = (gf & GF_ROUND_OVER) != 0;
+        if (!was_over && !ps[player].dead) apply_keys<G, NTPB, 1>(ps[player], bd[player], tb, kw, nkeys);   // make_actions :138-147
+        const bool finalize = (flags & KF_FINALIZE) != 0;
+        if (finalize) {
+            const bool over = finish_actions_n<G, NTPB>(ps, bd, inc, np, tb, seed16, p.elapsed, gf);
+            gf = over ? (gf | GF_ENV_DONE) : (gf & ~GF_ENV_DONE);
+        }
+        const bool done = (gf & GF_ENV_DONE) != 0;
+        const bool you_dead = np > 1 && ps[opponent_index(player, np)].dead;
+        if (p.reward) p.reward[row] = (int8_t)reward_base(done, ps[player].dead, you_dead);
+        if (p.done) p.done[row] = done ? 1 : 0;
+        if (p.lines)
+            for (int pl = 0; pl < np; pl++) p.lines[(size_t)row * np + pl] = (uint8_t)ps[pl].reward;
+        if (expand) {
+            if (p.key_len_out) p.key_len_out[row] = (uint8_t)nkeys;
+            if (p.keys_out)
+                for (int j = 0; j < p.lmax_out; j++)
+                    p.keys_out[(size_t)row * p.lmax_out + j] = (j < KW * 8) ? (uint8_t)((kw[j >> 3] >> (4 * (j & 7))) & 15u) : 0;
+        } else if (finalize && !was_over && p.stats) {
+            unsigned long long* st = p.stats + (blockIdx.x % STAT_SLICES) * STAT_WORDS;
+            atomicAdd(&st[0], 1ull);
+            int lines = 0, alive = 0, last = -1;
+            for (int pl = 0; pl < np; pl++) { lines += ps[pl].reward; if (!ps[pl].dead) { alive++; last = pl; } }
+            if (lines) atomicAdd(&st[5], (unsigned long long)lines);
+            if (done) {
+                atomicAdd(&st[1], 1ull);
+                if (alive == 0) atomicAdd(&st[4], 1ull);
+                else if (alive == 1 && last < 2) atomicAdd(&st[2 + last], 1ull);
+            }
+        }
+        if (!expand && done && (p.reset_seeds || p.auto_reset))
+            do_reset(p.reset_seeds ? p.reset_seeds[i] : auto_seed(p.seed_base, (uint32_t)gi, ps[0].episode));
+    }
+    if (p.stats) {
+        int flags_after = 0;
+        for (int pl = 0; pl < np; pl++) flags_after |= ps[pl].flags;
+        const int fresh = flags_after & ~flags_before;
+        if (fresh & 1) atomicAdd(&p.stats[(blockIdx.x % STAT_SLICES) * STAT_WORDS + 6], 1ull);
+        if (fresh & 2) atomicAdd(&p.stats[(blockIdx.x % STAT_SLICES) * STAT_WORDS + 7], 1ull);
+    }
+    if ((flags & KF_STORE) && !expand) {
+        for (int pl = 0; pl < np; pl++) {
+            const int base = pl * G::PW;
+            for (int c = 0; c < G::W; c++) {
+                const col_t v = bd[pl].col(c);
+                if (G::CW == 1) words[widx(base + c)] = (uint32_t)v;
+                else { words[widx(base + 2 * c)] = (uint32_t)v; words[widx(base + 2 * c + 1)] = (uint32_t)((uint64_t)v >> 32); }
+            }
+            for (int j = 0; j < G::SW; j++) words[widx(base + W0 + j)] = bd[pl].sw(j);
+            uint32_t sc[SCALAR_WORDS];
+            ps_pack(ps[pl], sc);
+            if (pl == 0) sc[0] |= ((uint32_t)gf & 15u) << 26;
+            for (int k = 0; k < 14; k++) words[widx(base + SCAL0 + k)] = sc[k];
+            for (int j = 0; j < GQ_WORDS; j++) words[widx(base + SCAL0 + 14 + j)] = ps[pl].gq[j * NTPB];
+            words[widx(base + SCAL0 + 23)] = __float_as_uint(inc[pl]);
+        }
+    }
+    // ---- outputs, player-index order: [rows, np, H, W] / [rows, np, 19] / [rows, np] / [rows, np, 8]
+    if (p.field) {
+        uint8_t* f = p.field + (size_t)row * np * G::FIELD_BYTES;
+        for (int pl = 0; pl < np; pl++)
+            for (int j = 0; j < G::SW; j++) {
+                const uint32_t w = bd[pl].sw(j);
+                for (int b = 0; b < 32 && j * 32 + b < G::FIELD_BYTES; b++) f[pl * G::FIELD_BYTES + j * 32 + b] = (uint8_t)((w >> b) & 1u);
+            }
+    }
+    if (p.vec)
+        for (int pl = 0; pl < np; pl++) observe_vec(ps[pl], p.vec + ((size_t)row * np + pl) * VEC_LEN);
+    if (p.piece_idx)
+        for (int pl = 0; pl < np; pl++) p.piece_idx[(size_t)row * np + pl] = (uint8_t)ps[pl].kind;
+    if (p.scalars)
+        for (int pl = 0; pl < np; pl++) {
+            int32_t* sv = p.scalars + ((size_t)row * np + pl) * 8;
+            const PS& q = ps[pl];
+            sv[0] = q.x; sv[1] = q.y; sv[2] = q.inc_count; sv[3] = q.remaining; sv[4] = q.combo_count; sv[5] = q.next; sv[6] = q.reward; sv[7] = q.dead;
+        }
+}
+
 // ---------------------------------------------------------------------------------------------- traffic probe
 // The HBM traffic of one fused step and nothing else: every thread reads its game's NV vectors and its key row, writes the vectors
 // back and the warp writes 32 rows of observation bytes, with the step kernel's own access pattern (tiles, coalesced 128-bit
@@ -1226,6 +1432,8 @@ struct GeomOps {
     cudaError_t (*launch_enum)(const EParams&, cudaStream_t);
     cudaError_t (*launch_unpack)(const uint32_t*, const int32_t*, const int32_t*, int, int, int, int, uint8_t*, uint8_t*, cudaStream_t);
     cudaError_t (*launch_init)(uint4*, int, cudaStream_t);
+    cudaError_t (*launch_gamen)(const KParams&, int rows, cudaStream_t);     // any player count (gamen_kernel)
+    int PW;                       // state words per player
     cudaError_t (*launch_traffic)(uint4*, int, const uint8_t*, int, const uint8_t*, const uint8_t*, const uint32_t*, int8_t*, uint8_t*, uint8_t*,
                                   uint8_t*, uint8_t*, uint8_t*, int, cudaStream_t);
     void (*decode)(const uint32_t* words, b2t_game_raw* out, uint8_t* field, const uint32_t* planes);          // host codec, b2t_raw.cuh
@@ -1243,6 +1451,8 @@ template <class G> struct Launch {
         e = cudaFuncSetAttribute(game_kernel<G, GM_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::GAME_TOTAL);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(enumerate_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, EnumCfg<G>::SMEM);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(gamen_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayoutN<G>::total(MAX_PLAYERS));
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(traffic_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::GAME_TOTAL);
         if (e != cudaSuccess) return e;
@@ -1274,6 +1484,11 @@ template <class G> struct Launch {
         init_kernel<G><<<(n + TPB - 1) / TPB, TPB, L::GAME_TOTAL, s>>>(state, n);
         return cudaGetLastError();
     }
+    static cudaError_t gamen(const KParams& p, int rows, cudaStream_t s) {
+        if (rows <= 0) return cudaSuccess;
+        gamen_kernel<G><<<(rows + NTPB - 1) / NTPB, NTPB, SmemLayoutN<G>::total(p.np), s>>>(p);
+        return cudaGetLastError();
+    }
     static cudaError_t traffic(uint4* state, int n, const uint8_t* keys, int lmax, const uint8_t* player, const uint8_t* key_len,
                                const uint32_t* seeds, int8_t* reward, uint8_t* done, uint8_t* lines, uint8_t* field, uint8_t* vec,
                                uint8_t* piece_idx, int step_like, cudaStream_t s) {
@@ -1284,7 +1499,7 @@ template <class G> struct Launch {
     }
     static const GeomOps* ops() {
         static const GeomOps o = {G::H, G::W, G::NV, G::KMAX, G::KEYW, G::LMAX, L::GAME_TOTAL, EnumCfg<G>::SMEM,
-                                  &prepare, &game, &enumerate, &unpack, &init, &traffic, &decode_game<G>, &encode_game<G>, 2 * TILE_PLANES * G::SW};
+                                  &prepare, &game, &enumerate, &unpack, &init, &gamen, G::PW, &traffic, &decode_game<G>, &encode_game<G>, 2 * TILE_PLANES * G::SW};
         return &o;
     }
 };

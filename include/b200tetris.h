@@ -19,6 +19,8 @@
  *   - h_* arrays may have any alignment; the zero-copy path of b2t_step_host is only taken when every array is naturally
  *     aligned for its element type and pinned over its whole length.
  *   - a handle is not thread-safe (neither is the reference); handles on different devices are independent.
+ *   - array shapes below are written for two players ([rows, 2, ...]); a handle created with another n_players has that many
+ *     entries on the player axis.
  *   - there is NO CPU fallback: without a CUDA device b2t_create fails with B2T_ERR_CUDA.
  */
 #ifndef B200TETRIS_H
@@ -38,7 +40,7 @@ extern "C" {
 typedef enum {
     B2T_OK = 0,
     B2T_ERR_ARG = -1,          /* bad argument (NULL, range, alignment) */
-    B2T_ERR_UNSUPPORTED = -2,  /* field size not instantiated (csrc/b2t_geoms.h) or n_players != 2 */
+    B2T_ERR_UNSUPPORTED = -2,  /* field size not instantiated (csrc/b2t_geoms.h), n_players outside 1..4, or a two-player-only feature */
     B2T_ERR_CUDA = -3,         /* CUDA runtime error (no device, launch failure, out of memory) */
     B2T_ERR_CAPACITY = -4,     /* caller buffer too small for the result */
     B2T_ERR_STATE = -5         /* call order (e.g. step by placement index without a prior enumerate) */
@@ -47,7 +49,11 @@ typedef enum {
 /* Settings of tetris_environment (experiments/presets.py:123-182 "default") that reach the backend. */
 typedef struct {
     int32_t n_games;             /* n_envs of tetris_environment_vector (tetris_environment_vector.py:10-17) */
-    int32_t n_players;           /* settings["n_players"]; only 2 is built */
+    int32_t n_players;           /* settings["n_players"]: 1..4 (PythonHandle.cpp:5-25).  2 is what every preset of the reference uses and
+                                    what the fast kernels serve; 1, 3 and 4 run on a plain compatibility kernel with the same rules:
+                                    axis 1 of every per-player array then has n_players entries, observations are B2T_U8 in
+                                    player-index order, keys are B2T_KEYS_U8, and b2t_get_game / b2t_set_game / B2T_FLAG_TILES
+                                    (whose structures describe two players) answer B2T_ERR_UNSUPPORTED */
     int32_t height, width;       /* settings["game_size"] = [H, W] (PythonHandle.cpp:5-8) */
     uint8_t piece_map[7];        /* (settings["pieces"]*7)[:7]  (tetris_environment.py:191-193 -> set_pieces) */
     uint8_t bar_null_moves;      /* settings["bar_null_moves"] (action_list remove_null) */
@@ -72,7 +78,7 @@ typedef struct {
     int32_t kmax;           /* capacity of a placement list */
     int32_t lmax;           /* capacity of a key sequence */
     int32_t state_bytes;    /* bytes of packed state per game in HBM */
-    int32_t obs_bytes;      /* 2*(H*W + 19 + 1) */
+    int32_t obs_bytes;      /* n_players*(H*W + 19 + 1) */
     int32_t tile_bytes;     /* bytes of colour planes per game (0 without B2T_FLAG_TILES) */
 } b2t_info;
 

@@ -794,7 +794,10 @@ void tor_step(tor_vec *v, const int32_t *idx, int n, const uint8_t *player, cons
         /* reward_fcn, tetris_environment.py:135-149 (extra_rewards=False) */
         int base = 0;
         if (g->env_done) {
-            int me = g->pl[pl].dead != 0, you = (v->np > 1) ? (g->pl[1 - pl].dead != 0) : 0;
+            /* backend.states[1 - player] is a PYTHON index (tetris_environment.py:139): for players beyond the second it counts
+             * from the end of the list — player 2 of 3 reads itself, player 3 of 4 reads player 2 */
+            int opp = 1 - pl >= 0 ? 1 - pl : v->np + (1 - pl);
+            int me = g->pl[pl].dead != 0, you = (v->np > 1) ? (g->pl[opp].dead != 0) : 0;
             base = you - me;
             if (me && you) base = -1;
         }

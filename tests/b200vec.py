@@ -7,10 +7,10 @@ from b200tetris import Engine
 
 
 class B200Vector:
-    def __init__(self, n_games, height=22, width=10, pieces=(0, 1, 2, 3, 4, 5, 6), bar_null_moves=True, **kw):
-        self.n, self.H, self.W, self.P = n_games, height, width, 2
+    def __init__(self, n_games, height=22, width=10, pieces=(0, 1, 2, 3, 4, 5, 6), bar_null_moves=True, n_players=2, **kw):
+        self.n, self.H, self.W, self.P = n_games, height, width, n_players
         self.bar_null = bar_null_moves
-        self.e = Engine(n_games, height, width, pieces, bar_null_moves=bar_null_moves, **kw)
+        self.e = Engine(n_games, height, width, pieces, n_players=n_players, bar_null_moves=bar_null_moves, **kw)
 
     def reset(self, seeds, idx=None):
         self.e.reset(seeds, idx)
@@ -35,9 +35,9 @@ class B200Vector:
         n = self.n if idx is None else len(idx)
         o = self.e.expand(player, idx, finalize=finalize, time_ms=time_ms, lmax=lmax)
         out = dict(K=o["K"], keys=np.zeros((n, kmax, lmax), np.uint8), key_len=np.zeros((n, kmax), np.uint8),
-                   reward=np.zeros((n, kmax), np.int8), done=np.zeros((n, kmax), np.uint8), lines=np.zeros((n, kmax, 2), np.uint8),
-                   field=np.zeros((n, kmax, 2, self.H, self.W), np.uint8), vec=np.zeros((n, kmax, 2, 19), np.uint8),
-                   piece_idx=np.zeros((n, kmax, 2), np.uint8), bad=0, total=o["total"], offsets=o["offsets"])
+                   reward=np.zeros((n, kmax), np.int8), done=np.zeros((n, kmax), np.uint8), lines=np.zeros((n, kmax, self.P), np.uint8),
+                   field=np.zeros((n, kmax, self.P, self.H, self.W), np.uint8), vec=np.zeros((n, kmax, self.P, 19), np.uint8),
+                   piece_idx=np.zeros((n, kmax, self.P), np.uint8), bad=0, total=o["total"], offsets=o["offsets"])
         assert o["offsets"][0] == 0 and np.array_equal(np.diff(o["offsets"]), o["K"])
         for i in range(n):
             a, b = o["offsets"][i], o["offsets"][i + 1]

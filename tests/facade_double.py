@@ -15,9 +15,8 @@ import pyhostsim  # noqa: E402
 
 class HostSimEngine:
     def __init__(self, n_games, height, width, pieces, n_players=2, bar_null_moves=True, time_ms_per_action=400, device=0, tiles=False):
-        assert n_players == 2
         self.bar_null, self.device = bool(bar_null_moves), device
-        self.v = pyhostsim.HostSimVector(n_games, height, width, pieces, tiles=tiles)
+        self.v = pyhostsim.HostSimVector(n_games, height, width, pieces, tiles=tiles, n_players=n_players)
         self.n, self.H, self.W = n_games, height, width
         self.kmax, self.lmax = (256, 128) if width > 10 else (96, 64)
         self.default_ms = time_ms_per_action
@@ -55,7 +54,7 @@ class HostSimEngine:
             out[name] = np.concatenate([o[name][i, :K[i]] for i in range(len(K))]) if len(K) else o[name][:0, 0]
         if want_scalars:   # only the `dead` column (7) is filled: it is the one the vector env reads from simulated outcomes
             dead = np.concatenate([o["dead"][i, :K[i]] for i in range(len(K))]) if len(K) else o["dead"][:0, 0]
-            out["scalars"] = np.zeros((len(dead), 2, 8), np.int32)
+            out["scalars"] = np.zeros((len(dead), dead.shape[1] if dead.ndim > 1 else 2, 8), np.int32)
             out["scalars"][:, :, 7] = dead
         return out
 
@@ -67,10 +66,14 @@ class HostSimEngine:
             self.import_state(i, b)
 
     def export_state(self, game):
+        if self.v.P != 2:
+            return (self.v.get_blob(game),)
         raw, field = self.v.get_game(game)
         return (bytes(raw), field.tobytes())
 
     def import_state(self, game, buf):
+        if self.v.P != 2:
+            return self.v.set_blob(game, buf[0])
         from b200tetris import _lib as abi
         raw = abi.GameRaw.from_buffer_copy(buf[0])
         self.v.set_game(game, raw, np.frombuffer(buf[1], np.uint8).reshape(2, self.H, self.W).copy())

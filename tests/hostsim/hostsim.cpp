@@ -38,6 +38,9 @@ struct HSBase {
     virtual int nwords() = 0;
     virtual void enable_tiles() = 0;
     virtual uint32_t* planes_of(int game) = 0;
+    virtual int blob_bytes() { return 0; }                       // opaque per-game snapshot (n-player simulator only)
+    virtual void get_blob(int, void*) {}
+    virtual void set_blob(int, const void*) {}
 };
 
 template <int KW> struct ListSink {
@@ -61,12 +64,8 @@ template <int KW> struct ListSink {
     }
 };
 
-template <int H, int W> struct HS : HSBase {
-    typedef Geo<H, W> G;
-    typedef typename G::col_t col_t;
-    static constexpr int KW = G::KEYW;
-    int n;
-    std::vector<uint32_t> state;  // uint4 state[NV][n]
+// piece / hole stream tables (filled lazily per seed), piece shapes, the combo power table: what DevTabs is on the device
+template <int W> struct HSTabs {
     PieceTables pt;
     uint8_t map[7];
     bool only_zs;
@@ -75,15 +74,7 @@ template <int H, int W> struct HS : HSBase {
     std::vector<uint8_t> row_ready;
     double powtab[256];
     Tabs tb;
-    col_t cols[2][G::NCOL];
-    uint32_t stream[2][G::SW];
-    uint32_t gqw[2][GQ_WORDS];
-    std::vector<uint32_t> tiles;   // optional colour planes [n][2][TILE_PLANES][SW] (B2T_FLAG_TILES of the product)
-    static constexpr int TW = 2 * TILE_PLANES * G::SW;
-    void enable_tiles() override { tiles.assign((size_t)n * TW, 0u); }
-    uint32_t* planes_of(int gi) override { return tiles.empty() ? nullptr : tiles.data() + (size_t)gi * TW; }
-
-    HS(int n_, const uint8_t* map_, uint32_t plen, uint32_t hlen) : n(n_), piece_len(plen), hole_len(hlen) {
+    HSTabs(const uint8_t* map_, uint32_t plen, uint32_t hlen) : piece_len(plen), hole_len(hlen) {
         memcpy(map, map_, 7);
         only_zs = true;
         for (int i = 0; i < 7; i++) if (map[i] != 2 && map[i] != 3) only_zs = false;
@@ -95,6 +86,32 @@ template <int H, int W> struct HS : HSBase {
         tb.pcn = pt.pcn; tb.pcc = pt.pcc; tb.piece = piece_tab.data(); tb.hole = hole_tab.data(); tb.powtab = powtab;
         tb.piece_len = piece_len; tb.hole_len = hole_len; tb.spawn_rots = 0;
         for (int k = 0; k < 7; k++) tb.spawn_rots |= (uint32_t)pt.spawn_rot[k] << (2 * k);
+    }
+    void ensure_row(uint32_t s16) {
+        if (row_ready[s16]) return;
+        static MT19937 mt;
+        fill_stream_row(mt, s16, map, only_zs, W, &piece_tab[(size_t)s16 * piece_len], piece_len, &hole_tab[(size_t)s16 * hole_len], hole_len);
+        row_ready[s16] = 1;
+    }
+};
+
+template <int H, int W> struct HS : HSBase, HSTabs<W> {
+    typedef Geo<H, W> G;
+    typedef typename G::col_t col_t;
+    static constexpr int KW = G::KEYW;
+    using HSTabs<W>::tb;
+    using HSTabs<W>::ensure_row;
+    int n;
+    std::vector<uint32_t> state;  // uint4 state[NV][n]
+    col_t cols[2][G::NCOL];
+    uint32_t stream[2][G::SW];
+    uint32_t gqw[2][GQ_WORDS];
+    std::vector<uint32_t> tiles;   // optional colour planes [n][2][TILE_PLANES][SW] (B2T_FLAG_TILES of the product)
+    static constexpr int TW = 2 * TILE_PLANES * G::SW;
+    void enable_tiles() override { tiles.assign((size_t)n * TW, 0u); }
+    uint32_t* planes_of(int gi) override { return tiles.empty() ? nullptr : tiles.data() + (size_t)gi * TW; }
+
+    HS(int n_, const uint8_t* map_, uint32_t plen, uint32_t hlen) : HSTabs<W>(map_, plen, hlen), n(n_) {
         state.assign(state_vectors<G>(n) * 4, 0);
         Game<G, 1> g;
         bind(g);
@@ -105,12 +122,6 @@ template <int H, int W> struct HS : HSBase {
             g.b[p].cols = cols[p]; g.b[p].stream = stream[p]; g.p[p].gq = gqw[p];
             board_init_walls<G, 1>(g.b[p]);
         }
-    }
-    void ensure_row(uint32_t s16) {
-        if (row_ready[s16]) return;
-        static MT19937 mt;
-        fill_stream_row(mt, s16, map, only_zs, W, &piece_tab[(size_t)s16 * piece_len], piece_len, &hole_tab[(size_t)s16 * hole_len], hole_len);
-        row_ready[s16] = 1;
     }
     void load(Game<G, 1>& g, int gi) {
         for (int p = 0; p < 2; p++) g.b[p].tiles = tiles.empty() ? nullptr : planes_of(gi) + p * TILE_PLANES * G::SW;
@@ -295,9 +306,199 @@ template <int H, int W> struct HS : HSBase {
     }
 };
 
+// n_players != 2: the rules of b2t_core.cuh's "any number of players" section (what gamen_kernel runs on the device), games kept
+// unpacked.  The per-game raw codec, colour planes and word views describe two players and are not offered here.
+template <int H, int W> struct HSN : HSBase, HSTabs<W> {
+    typedef Geo<H, W> G;
+    typedef typename G::col_t col_t;
+    static constexpr int KW = G::KEYW;
+    using HSTabs<W>::tb;
+    using HSTabs<W>::ensure_row;
+    struct GameN {
+        PS p[MAX_PLAYERS];
+        col_t cols[MAX_PLAYERS][G::NCOL];
+        uint32_t stream[MAX_PLAYERS][G::SW];
+        uint32_t gq[MAX_PLAYERS][GQ_WORDS];
+        float inc[MAX_PLAYERS];
+        int gf;
+        uint32_t seed16;
+    };
+    int n, np;
+    std::vector<GameN> games;
+    HSN(int n_, int np_, const uint8_t* map_, uint32_t plen, uint32_t hlen) : HSTabs<W>(map_, plen, hlen), n(n_), np(np_), games(n_) {
+        for (auto& g : games) {
+            memset(&g, 0, sizeof g);
+            Board<G, 1> bd[MAX_PLAYERS];
+            bind(g, bd);
+            for (int pl = 0; pl < np; pl++) {
+                board_init_walls<G, 1>(bd[pl]);
+                board_clear<G, 1>(bd[pl]);
+                g.p[pl].kind = 7; g.p[pl].min_remaining = 1000; g.p[pl].drop_delay = 1000;
+            }
+        }
+    }
+    void bind(GameN& g, Board<G, 1>* bd) {
+        for (int pl = 0; pl < np; pl++) { bd[pl].cols = g.cols[pl]; bd[pl].stream = g.stream[pl]; bd[pl].tiles = nullptr; g.p[pl].gq = g.gq[pl]; }
+    }
+    void reset(const int32_t* idx, int cnt, const uint32_t* seeds) override {
+        for (int i = 0; i < cnt; i++) {
+            GameN& g = games[idx ? idx[i] : i];
+            Board<G, 1> bd[MAX_PLAYERS];
+            bind(g, bd);
+            ensure_row(seeds[i] & 0xFFFF);
+            g.seed16 = seeds[i] & 0xFFFF;
+            reset_game_n<G, 1>(g.p, bd, g.inc, np, tb, g.seed16, g.gf);
+        }
+    }
+    bool perform(GameN& g, int player, const uint32_t* kw, int nkeys, bool finalize, int time_ms, int* reward) {
+        Board<G, 1> bd[MAX_PLAYERS];
+        bind(g, bd);
+        if (player >= np) player = np - 1;
+        if (!(g.gf & GF_ROUND_OVER) && !g.p[player].dead) apply_keys<G, 1, 1>(g.p[player], bd[player], tb, kw, nkeys);
+        if (finalize) {
+            const bool over = finish_actions_n<G, 1>(g.p, bd, g.inc, np, tb, g.seed16, time_ms, g.gf);
+            g.gf = over ? (g.gf | GF_ENV_DONE) : (g.gf & ~GF_ENV_DONE);
+        }
+        const bool done = (g.gf & GF_ENV_DONE) != 0;
+        const bool you_dead = np > 1 && g.p[opponent_index(player, np)].dead;
+        *reward = reward_base(done, g.p[player].dead, you_dead);
+        return done;
+    }
+    void step(const int32_t* idx, int cnt, const uint8_t* player, const uint8_t* keys, const uint8_t* key_len, int lmax, int time_ms,
+              int finalize, int8_t* reward, uint8_t* done, uint8_t* lines) override {
+        for (int i = 0; i < cnt; i++) {
+            GameN& g = games[idx ? idx[i] : i];
+            uint32_t kw[KW];
+            pack_keys<KW>(keys + (size_t)i * lmax, key_len[i], kw);
+            int r;
+            const bool d = perform(g, player[i], kw, key_len[i], finalize != 0, time_ms, &r);
+            if (reward) reward[i] = (int8_t)r;
+            if (done) done[i] = d;
+            if (lines) for (int pl = 0; pl < np; pl++) lines[(size_t)i * np + pl] = (uint8_t)g.p[pl].reward;
+        }
+    }
+    void obs_of(GameN& g, uint8_t* field, uint8_t* vec, uint8_t* pidx) {
+        Board<G, 1> bd[MAX_PLAYERS];
+        bind(g, bd);
+        for (int pl = 0; pl < np; pl++) {
+            if (field)
+                for (int c = 0; c < H * W; c++) field[pl * H * W + c] = (bd[pl].sw(c >> 5) >> (c & 31)) & 1;
+            if (vec) observe_vec(g.p[pl], vec + pl * VEC_LEN);
+            if (pidx) pidx[pl] = (uint8_t)g.p[pl].kind;
+            for (int y = 0; y < H; y++)       // the two board forms (columns vs stream) must agree
+                for (int x = 0; x < W; x++)
+                    if ((int)((bd[pl].col(x) >> (y + G::YB)) & 1) != (int)((bd[pl].sw((y * W + x) >> 5) >> ((y * W + x) & 31)) & 1)) abort();
+        }
+    }
+    void observe(const int32_t* idx, int cnt, uint8_t* field, uint8_t* vec, uint8_t* pidx) override {
+        for (int i = 0; i < cnt; i++)
+            obs_of(games[idx ? idx[i] : i], field ? field + (size_t)i * np * H * W : nullptr, vec ? vec + (size_t)i * np * VEC_LEN : nullptr,
+                   pidx ? pidx + (size_t)np * i : nullptr);
+    }
+    void scal(const int32_t* idx, int cnt, int32_t* out) override {
+        for (int i = 0; i < cnt; i++) {
+            GameN& g = games[idx ? idx[i] : i];
+            for (int pl = 0; pl < np; pl++) {
+                int32_t* s = out + ((size_t)i * np + pl) * 8;
+                const PS& q = g.p[pl];
+                s[0] = q.x; s[1] = q.y; s[2] = q.inc_count; s[3] = q.remaining; s[4] = q.combo_count; s[5] = q.next; s[6] = q.reward; s[7] = q.dead;
+            }
+        }
+    }
+    int enum_game(GameN& g, int player, int bar_null, uint32_t* lst, int cap, int* bad) {
+        Board<G, 1> bd[MAX_PLAYERS];
+        bind(g, bd);
+        if (player >= np) player = np - 1;
+        ListSink<KW> sink;
+        const int off = bar_null ? 0 : 1;
+        for (int i = 0; i < KW; i++) lst[i] = 0;
+        sink.init(lst + off * KW, cap - off);
+        const PS& me = g.p[player];
+        if (me.kind <= 6) {
+            uint8_t pbuf[EnumGeo<G>::PCAP];
+            Enumerator<G, 1, KW, ListSink<KW>> e(bd[player], tb, me.kind, sink, pbuf);
+            e.run(me.rot);
+        }
+        *bad = sink.bad;
+        if (sink.count == 0) { for (int i = 0; i < KW; i++) lst[i] = 0; return 1; }
+        return sink.count + off;
+    }
+    static void unpack_seq(const uint32_t* w, uint8_t* keys, uint8_t* len, int lmax) {
+        const int L = packed_len<KW>(w);
+        memset(keys, 0, lmax);
+        for (int i = 0; i < L && i < lmax; i++) keys[i] = (w[i >> 3] >> (4 * (i & 7))) & 15;
+        *len = (uint8_t)(L < lmax ? L : lmax);
+    }
+    int enumerate(const int32_t* idx, int cnt, const uint8_t* player, int bar_null, int kmax, int lmax, int32_t* K, uint8_t* keys,
+                  uint8_t* key_len) override {
+        std::vector<uint32_t> lst((size_t)(kmax + 1) * KW);
+        int nbad = 0;
+        for (int i = 0; i < cnt; i++) {
+            int bad;
+            const int k = enum_game(games[idx ? idx[i] : i], player[i], bar_null, lst.data(), kmax, &bad);
+            K[i] = k; nbad += bad;
+            for (int a = 0; a < kmax; a++) {
+                uint8_t* dst = keys + ((size_t)i * kmax + a) * lmax;
+                if (a < k) unpack_seq(&lst[(size_t)a * KW], dst, &key_len[(size_t)i * kmax + a], lmax);
+                else { memset(dst, 0, lmax); key_len[(size_t)i * kmax + a] = 0; }
+            }
+        }
+        return nbad;
+    }
+    int expand(const int32_t* idx, int cnt, const uint8_t* player, int bar_null, int finalize, int time_ms, int kmax, int lmax, int32_t* K,
+               uint8_t* keys, uint8_t* key_len, uint8_t* field, uint8_t* vec, uint8_t* pidx, int8_t* reward, uint8_t* done,
+               uint8_t* lines, uint8_t* dead) override {
+        std::vector<uint32_t> lst((size_t)(kmax + 1) * KW);
+        int nbad = 0;
+        for (int i = 0; i < cnt; i++) {
+            const GameN& base = games[idx ? idx[i] : i];
+            GameN g = base;
+            int bad;
+            const int k = enum_game(g, player[i], bar_null, lst.data(), kmax, &bad);
+            K[i] = k; nbad += bad;
+            for (int a = 0; a < kmax; a++) {
+                const size_t o = (size_t)i * kmax + a;
+                uint8_t* dst = keys + o * lmax;
+                if (a >= k) { memset(dst, 0, lmax); key_len[o] = 0; continue; }
+                unpack_seq(&lst[(size_t)a * KW], dst, &key_len[o], lmax);
+                g = base;
+                int r;
+                const bool d = perform(g, player[i], &lst[(size_t)a * KW], packed_len<KW>(&lst[(size_t)a * KW]), finalize != 0, time_ms, &r);
+                if (reward) reward[o] = (int8_t)r;
+                if (done) done[o] = d;
+                for (int pl = 0; pl < np; pl++) {
+                    if (lines) lines[o * np + pl] = (uint8_t)g.p[pl].reward;
+                    if (dead) dead[o * np + pl] = (uint8_t)g.p[pl].dead;
+                }
+                obs_of(g, field ? field + o * np * H * W : nullptr, vec ? vec + o * np * VEC_LEN : nullptr, pidx ? pidx + np * o : nullptr);
+            }
+        }
+        return nbad;
+    }
+    int flags(int gi) override { int f = 0; for (int pl = 0; pl < np; pl++) f |= games[gi].p[pl].flags; return f; }
+    void get_game(int, b2t_game_raw*, uint8_t*) override { abort(); }          // b2t_game_raw describes two players
+    void set_game(int, const b2t_game_raw*, const uint8_t*) override { abort(); }
+    void copy_game(int dst, HSBase* from, int src) override { games[dst] = static_cast<HSN*>(from)->games[src]; ensure_row(games[dst].seed16); }
+    void words_of(int, uint32_t*) override { abort(); }
+    int nwords() override { return 0; }
+    void enable_tiles() override {}
+    uint32_t* planes_of(int) override { return nullptr; }
+    int blob_bytes() override { return (int)sizeof(GameN); }
+    void get_blob(int gi, void* out) override { memcpy(out, &games[gi], sizeof(GameN)); }
+    void set_blob(int gi, const void* in) override { memcpy(&games[gi], in, sizeof(GameN)); ensure_row(games[gi].seed16); }
+};
+
 extern "C" {
 void* hs_create(int n, int H, int W, const uint8_t* map, uint32_t piece_len, uint32_t hole_len) {
 #define X(h, w) if (H == h && W == w) return (HSBase*)new HS<h, w>(n, map, piece_len, hole_len);
+    B2T_FOR_EACH_GEOMETRY(X)
+#undef X
+    return nullptr;
+}
+void* hs_create_players(int n, int n_players, int H, int W, const uint8_t* map, uint32_t piece_len, uint32_t hole_len) {
+    if (n_players == 2) return hs_create(n, H, W, map, piece_len, hole_len);
+    if (n_players < 1 || n_players > MAX_PLAYERS) return nullptr;
+#define X(h, w) if (H == h && W == w) return (HSBase*)new HSN<h, w>(n, n_players, map, piece_len, hole_len);
     B2T_FOR_EACH_GEOMETRY(X)
 #undef X
     return nullptr;
@@ -324,4 +525,7 @@ void hs_get_game(void* h, int game, b2t_game_raw* out, uint8_t* field) { ((HSBas
 void hs_set_game(void* h, int game, const b2t_game_raw* in, const uint8_t* field) { ((HSBase*)h)->set_game(game, in, field); }
 void hs_enable_tiles(void* h) { ((HSBase*)h)->enable_tiles(); }
 void hs_copy_game(void* to, int dst, void* from, int src) { ((HSBase*)to)->copy_game(dst, (HSBase*)from, src); }
+int hs_blob_bytes(void* h) { return ((HSBase*)h)->blob_bytes(); }
+void hs_get_blob(void* h, int game, void* out) { ((HSBase*)h)->get_blob(game, out); }
+void hs_set_blob(void* h, int game, const void* in) { ((HSBase*)h)->set_blob(game, in); }
 }

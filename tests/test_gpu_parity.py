@@ -436,7 +436,7 @@ def test_edge_cases_through_the_abi():
         Engine(4, 23, 11)
     assert e.value.code == _lib.ERR_UNSUPPORTED
     with pytest.raises(B2TError) as e:
-        Engine(4, n_players=3)
+        Engine(4, n_players=5)
     assert e.value.code == _lib.ERR_UNSUPPORTED
     with pytest.raises(B2TError) as e:
         Engine(0)

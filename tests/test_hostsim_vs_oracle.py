@@ -121,3 +121,36 @@ def test_stream_tables_match_oracle():
             keys = np.zeros((1, 32), np.uint8)
             got = [int(sim.observe()[2][0, 0]), int(np.argmax(sim.observe()[1][0, 0, 5:12]))]
             assert got == [want[0], want[1]]
+
+
+N_PLAYERS = [  # n_players, kind, H, W, pieces, games, steps — the rules gamen_kernel runs for handles with 1, 3 or 4 players
+    (1, "random", 22, 10, (0, 1, 2, 3, 4, 5, 6), 24, 300),
+    (1, "greedy", 22, 10, (0, 1, 2, 3, 4, 5, 6), 8, 400),
+    (3, "random", 22, 10, (0, 1, 2, 3, 4, 5, 6), 32, 300),
+    (3, "greedy", 22, 10, (0, 1, 2, 3, 4, 5, 6), 8, 600),
+    (3, "junk", 22, 10, (0, 1, 2, 3, 4, 5, 6), 16, 300),
+    (3, "press_key", 22, 10, (0, 1, 2, 3, 4, 5, 6), 12, 600),
+    (4, "greedy", 22, 10, (0, 1, 2, 3, 4, 5, 6), 6, 600),
+    (4, "random", 16, 8, (0, 6), 24, 300),
+    (3, "greedy", 40, 20, (0, 1, 2, 3, 4, 5, 6), 2, 200),
+    (4, "junk", 25, 12, (0, 1, 2, 3, 4, 5, 6), 6, 200),
+]
+
+
+@pytest.mark.parametrize("P,kind,H,W,pieces,n,steps", N_PLAYERS)
+def test_core_matches_oracle_for_other_player_counts(P, kind, H, W, pieces, n, steps):
+    """distributeLines' float split among all the others, solo rounds, the reward rule's Python index"""
+    kmax, lmax = (256, 64) if W > 10 else (96, 32)
+    lead = pyoracle.OracleVector(n, H, W, pieces, n_players=P)
+    sim = pyhostsim.HostSimVector(n, H, W, pieces, n_players=P)
+    stats = harness.rollout_pair(lead, sim, steps, harness.Policy(kind, kmax=kmax, lmax=lmax, n_players=P))
+    assert stats["steps"] == n * steps
+    assert all(sim.flags(i) == 0 for i in range(n))
+    if kind == "greedy" and P > 1 and W >= 8:
+        assert stats["lines"] > 0 and stats["garbage"] > 0, stats
+    player = (np.arange(n) % P).astype(np.uint8)
+    for fin in (True, False):
+        a = lead.expand(player, finalize=fin, kmax=kmax, lmax=lmax)
+        b = sim.expand(player, finalize=fin, kmax=kmax, lmax=lmax)
+        for k in ("K", "keys", "key_len", "reward", "done", "lines", "field", "vec", "piece_idx"):
+            assert np.array_equal(a[k], b[k]), (fin, k)

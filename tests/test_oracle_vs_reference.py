@@ -118,6 +118,8 @@ N_PLAYERS = [  # n_players, kind, H, W, games, steps: PythonHandle with 1, 3 and
     (3, "greedy", 22, 10, 4, 420),
     (3, "junk", 22, 10, 6, 200),
     (4, "greedy", 22, 10, 3, 420),
+    (4, "random", 22, 10, 16, 300),    # many rounds end with a late player to move: the reward rule's Python index (states[1 - player])
+    (3, "random", 16, 8, 16, 300),
     (4, "press_key", 22, 10, 4, 500),
     (3, "greedy", 16, 8, 4, 300),
 ]

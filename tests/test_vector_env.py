@@ -20,11 +20,12 @@ pytestmark = pytest.mark.skipif(not (os.path.isdir(os.path.join(REF, "environmen
 
 
 def dicts(state):
-    return [{k: np.array(v).tolist() for k, v in state[p].items()} for p in (0, 1)]
+    return [{k: np.array(v).tolist() for k, v in state[p].items()} for p in range(len(state))]
 
 
 @pytest.mark.parametrize("extra", [{}, {"game_size": [16, 8], "pieces": [0, 6], "bar_null_moves": False},
-                                   {"extra_rewards": True, "reward_ammount": (1.0, 0.25)}])
+                                   {"extra_rewards": True, "reward_ammount": (1.0, 0.25)},
+                                   {"n_players": 3}, {"n_players": 4, "game_size": [16, 8], "pieces": [0, 6]}])
 def test_vector_env_matches_the_reference_vector_env(extra):
     import facade_double
     facade_double.install()
@@ -33,7 +34,7 @@ def test_vector_env_matches_the_reference_vector_env(extra):
         te, tev = _reference_front_end()
         ref_mod, ref_time = refmod.load("B")
         te.tetris_env = ref_mod
-        n, T = 8, 120
+        n, T, P = 8, 120, extra.get("n_players", 2)
         ours = tetris_environment_vector(n, settings=dict(extra, seed=4242))
         ref_time(0)
         ref = tev.tetris_environment_vector(n, te.tetris_environment, settings=dict({"presets": ["default"], "render": False}, **extra))
@@ -50,7 +51,8 @@ def test_vector_env_matches_the_reference_vector_env(extra):
                 ref_time(int(s))
                 ref.reset(env=[int(i)])
         reset_reference(list(range(n)))
-        cur = np.arange(n) & 1
+        cur = np.arange(n) & 1            # (with more than two players only the first two can move through the reference's front-end:
+                                          #  its per-player lists have two entries, tetris_environment.py:28-29)
         n_sims = n_done = 0
         for t in range(T):
             cur = 1 - cur
@@ -63,7 +65,7 @@ def test_vector_env_matches_the_reference_vector_env(extra):
                 if t == 0:                  # combo.remaining is uninitialised in a fresh reference handle
                     for d in x + y:
                         d["combo_time"] = 0
-                assert x == y, (t, i, [(k, x[p][k], y[p][k]) for p in (0, 1) for k in x[p] if x[p][k] != y[p][k]])
+                assert x == y, (t, i, [(k, x[p][k], y[p][k]) for p in range(P) for k in x[p] if x[p][k] != y[p][k]])
                 assert [int(v) for v in s_ref[i].is_dead] == [int(v) for v in s_our[i].is_dead]
                 a_ref = ref.envs[i].get_actions(s_ref[i], player=players[i])
                 assert [list(a) for a in a_ref] == [list(a) for a in a_our[i]], (t, i)
@@ -86,8 +88,8 @@ def test_vector_env_matches_the_reference_vector_env(extra):
             assert [float(r()) for r in r_ref] == [float(r()) for r in r_our], t
             assert [bool(d) for d in d_ref] == [bool(d) for d in d_our], t
             for i in range(n):              # get_winner: the reference's reads an unbound attribute; its rule is :118-125
-                dead = [int(ref.envs[i].backend.states[p].dead[0]) for p in (0, 1)]
-                want = None if not d_ref[i] else ([p for p in (0, 1) if not dead[p]] + [666])[0]
+                dead = [int(ref.envs[i].backend.states[p].dead[0]) for p in range(P)]
+                want = None if not d_ref[i] else ([p for p in range(P) if not dead[p]] + [666])[0]
                 assert ours.get_winner(env=[i])[0] == want
             ended = [i for i, d in enumerate(d_ref) if d]
             if ended:
