@@ -241,7 +241,7 @@ static void base_params(b2t_handle* h, KParams& p) {
 }
 // the kernels of this handle's player count
 static cudaError_t launch_game(b2t_handle* h, const KParams& p, int rows, cudaStream_t s) {
-    return h->multi() ? h->ops->launch_gamen(p, rows, s) : launch_game(h, p, rows, s);
+    return h->multi() ? h->ops->launch_gamen(p, rows, s) : h->ops->launch_game(p, rows, s);
 }
 static int check_obs(b2t_handle* h, const b2t_obs& o) {
     if (!aligned16(o.d_field) || !aligned16(o.d_vec) || !aligned16(o.d_piece_idx) || !aligned16(o.d_scalars))
