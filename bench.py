@@ -11,7 +11,9 @@ Workload at N=1: BASELINE configs[3] sharded weakly — 2^20 concurrent games pe
 step, both far larger than the 126 MB L2, so no flush is needed between iterations); actions are SVENton key strings
 [8]*r+[2]+[3]*t+[7] (agents/sventon_agent/sventon_utils.py:9-13) drawn from a counter hash, resident in HBM before the
 timed region.  The all-placements world model (configs[2], 65 536 boards) is timed in the same run and reported under
-"placements".
+"placements" (also with bit-packed fields and on boards of a heuristic policy), the device-resident actor loop under "actor_loop",
+BASELINE configs[4] (custom field sizes) under "custom_sizes".  roofline.mix_peak is the step's own HBM traffic replayed without
+game logic (b2t_debug_traffic): what that read/write mix reaches on the device.
 """
 import argparse
 import json

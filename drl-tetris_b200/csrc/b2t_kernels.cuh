@@ -1237,10 +1237,18 @@ __global__ void __launch_bounds__(NTPB) gamen_kernel(const KParams p) {
         i = m.x; gi = m.y; sel = m.z; player = m.w;
     } else gi = p.idx ? p.idx[i] : i + p.game0;
     if ((unsigned)gi >= (unsigned)p.n_games) return;       // a foreign id: an inert row
-    uint32_t* words = reinterpret_cast<uint32_t*>(p.state);
-    const size_t tile = (size_t)(gi >> 5) * (size_t)p.nv;
-    auto widx = [&](int wi) { return ((tile + (size_t)(wi >> 2)) * 32 + (size_t)(gi & 31)) * 4 + (size_t)(wi & 3); };
+    // the game's nv vectors travel as 128-bit accesses (a warp's 32 games: 512 contiguous bytes per vector) through a per-thread
+    // word array in local memory, which the per-player loops below index freely
+    constexpr int LWORDS = 4 * ((MAX_PLAYERS * G::PW + 3) / 4);
+    uint32_t words[LWORDS];
+    uint4* gvec = p.state + ((size_t)(gi >> 5) * (size_t)p.nv) * 32 + (size_t)(gi & 31);
+    auto widx = [&](int wi) { return wi; };
     int gf = 0;
+    if (!(flags & KF_INIT))
+        for (int v = 0; v < p.nv; v++) {
+            const uint4 q = gvec[(size_t)v * 32];
+            words[4 * v] = q.x; words[4 * v + 1] = q.y; words[4 * v + 2] = q.z; words[4 * v + 3] = q.w;
+        }
     if (flags & KF_INIT) {
         for (int pl = 0; pl < np; pl++) {
             board_clear<G, NTPB>(bd[pl]);
@@ -1364,15 +1372,26 @@ __global__ void __launch_bounds__(NTPB) gamen_kernel(const KParams p) {
             for (int j = 0; j < GQ_WORDS; j++) words[widx(base + SCAL0 + 14 + j)] = ps[pl].gq[j * NTPB];
             words[widx(base + SCAL0 + 23)] = __float_as_uint(inc[pl]);
         }
+        for (int k = np * G::PW; k < 4 * p.nv; k++) words[k] = 0u;
+        for (int v = 0; v < p.nv; v++) gvec[(size_t)v * 32] = make_uint4(words[4 * v], words[4 * v + 1], words[4 * v + 2], words[4 * v + 3]);
     }
     // ---- outputs, player-index order: [rows, np, H, W] / [rows, np, 19] / [rows, np] / [rows, np, 8]
     if (p.field) {
         uint8_t* f = p.field + (size_t)row * np * G::FIELD_BYTES;
-        for (int pl = 0; pl < np; pl++)
-            for (int j = 0; j < G::SW; j++) {
-                const uint32_t w = bd[pl].sw(j);
-                for (int b = 0; b < 32 && j * 32 + b < G::FIELD_BYTES; b++) f[pl * G::FIELD_BYTES + j * 32 + b] = (uint8_t)((w >> b) & 1u);
-            }
+        if (G::FIELD_BYTES % 4 == 0 && (reinterpret_cast<uintptr_t>(p.field) & 3) == 0) {     // four cells per store
+            uint32_t* f4 = reinterpret_cast<uint32_t*>(f);
+            for (int pl = 0; pl < np; pl++)
+                for (int j = 0; j < G::SW; j++) {
+                    const uint32_t w = bd[pl].sw(j);
+                    for (int b = 0; b < 8 && j * 8 + b < G::FIELD_BYTES / 4; b++)
+                        f4[pl * (G::FIELD_BYTES / 4) + j * 8 + b] = (((w >> (4 * b)) & 15u) * 0x00204081u) & 0x01010101u;
+                }
+        } else
+            for (int pl = 0; pl < np; pl++)
+                for (int j = 0; j < G::SW; j++) {
+                    const uint32_t w = bd[pl].sw(j);
+                    for (int b = 0; b < 32 && j * 32 + b < G::FIELD_BYTES; b++) f[pl * G::FIELD_BYTES + j * 32 + b] = (uint8_t)((w >> b) & 1u);
+                }
     }
     if (p.vec)
         for (int pl = 0; pl < np; pl++) observe_vec(ps[pl], p.vec + ((size_t)row * np + pl) * VEC_LEN);
