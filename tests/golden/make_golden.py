@@ -27,13 +27,17 @@ CASES = {
     "c5_random_40x20": ("random", 40, 20, (0, 1, 2, 3, 4, 5, 6), 4, 250, 0),
     "c5_greedy_40x20": ("greedy", 40, 20, (0, 1, 2, 3, 4, 5, 6), 2, 200, 0),
     "zs_only_10x6": ("random", 10, 6, (2, 3), 8, 120, 0),
+    # other player counts (8th entry): PythonHandle with 3 / 4 / 1 players
+    "p3_greedy_22x10": ("greedy", 22, 10, (0, 1, 2, 3, 4, 5, 6), 6, 450, 0, 3),
+    "p4_random_22x10": ("random", 22, 10, (0, 1, 2, 3, 4, 5, 6), 12, 300, 0, 4),
+    "p1_greedy_22x10": ("greedy", 22, 10, (0, 1, 2, 3, 4, 5, 6), 6, 300, 0, 1),
 }
 
 
-def make(name, kind, H, W, pieces, n, T, solo):
+def make(name, kind, H, W, pieces, n, T, solo, P=2):
     kmax, lmax = (128, 64) if W > 10 else (64, 32)
-    lead = pyoracle.OracleVector(n, H, W, pieces)
-    ref = refdrive.RefVector(n, H, W, pieces)
+    lead = pyoracle.OracleVector(n, H, W, pieces, n_players=P)
+    ref = refdrive.RefVector(n, H, W, pieces, n_players=P)
     assert refdrive.reference_python() is not None, "needs /root/reference for action_list/state_dict"
     rec = dict(player=[], keys=[], key_len=[], reward=[], done=[], lines=[], K=[], enum_digest=[], obs_digest=[])
     snaps = dict(t=[], field=[], vec=[])
@@ -53,9 +57,9 @@ def make(name, kind, H, W, pieces, n, T, solo):
     def on_reset(t, ids, seeds):
         resets[t] = (ids.copy(), seeds.copy())
 
-    st = harness.rollout_pair(lead, ref, T, harness.Policy(kind, kmax=kmax, lmax=lmax, solo_period=solo),
+    st = harness.rollout_pair(lead, ref, T, harness.Policy(kind, kmax=kmax, lmax=lmax, solo_period=solo, n_players=P),
                               on_step=on_step, on_reset=on_reset, compare_hidden=True)
-    out = dict(n=n, T=T, H=H, W=W, pieces=np.array(pieces), kmax=kmax, lmax=lmax, policy=kind,
+    out = dict(n=n, T=T, H=H, W=W, n_players=P, pieces=np.array(pieces), kmax=kmax, lmax=lmax, policy=kind,
                seeds0=harness.seeds_for(np.arange(n), np.zeros(n, int)),
                reset_steps=np.array(sorted(resets), np.int64), snap_steps=np.array(snaps["t"], np.int64),
                snap_field=np.array(snaps["field"]), snap_vec=np.array(snaps["vec"]))

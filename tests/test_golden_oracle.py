@@ -15,7 +15,8 @@ GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.n
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
 def test_oracle_replays_golden(path):
     g = np.load(path)
-    eng = pyoracle.OracleVector(int(g["n"]), int(g["H"]), int(g["W"]), tuple(int(x) for x in g["pieces"]))
+    eng = pyoracle.OracleVector(int(g["n"]), int(g["H"]), int(g["W"]), tuple(int(x) for x in g["pieces"]),
+                                n_players=int(g["n_players"]) if "n_players" in g else 2)
     assert harness.replay_golden(eng, g) == int(g["n"]) * int(g["T"])
 
 

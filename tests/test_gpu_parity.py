@@ -77,7 +77,8 @@ GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.n
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
 def test_replays_reference_golden(path):
     g = np.load(path)
-    eng = _engine(int(g["n"]), int(g["H"]), int(g["W"]), tuple(int(x) for x in g["pieces"]))
+    eng = _engine(int(g["n"]), int(g["H"]), int(g["W"]), tuple(int(x) for x in g["pieces"]),
+                  n_players=int(g["n_players"]) if "n_players" in g else 2)
     harness.replay_golden(eng, g)
 
 
