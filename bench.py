@@ -482,8 +482,13 @@ def main():
         e2e_steps = max(2, min(a.steps, 30))
         import ctypes as C
         from b200tetris.engine import _hp
-        def pinned(t):   # numpy view of a pinned host copy of a device tensor
-            return t.cpu().pin_memory().numpy()
+        from b200tetris import host_array
+
+        def pinned(t):   # the step's INPUTS: pinned, write-combined host memory from b2t_host_alloc (the host only writes them; the device's reads skip the CPU cache snoop)
+            src = t.cpu().numpy() if hasattr(t, "cpu") else t
+            buf = host_array(src.shape, src.dtype, write_combined=True)
+            buf[...] = src
+            return buf
         hk = [(pinned(keys_r[t % R]), pinned(len_r[t % R]), pinned(seed_r[t % R]).view(np.uint32), pinned(player_r[t & 1])) for t in range(R)]
         h_rew = torch.empty(n, dtype=torch.int8).pin_memory().numpy(); h_done = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
         h_lines = torch.empty((n, 2), dtype=torch.uint8).pin_memory().numpy()
@@ -492,7 +497,7 @@ def main():
 
         def pack4(k):     # two 4-bit key tokens per byte, low nibble first (B2T_KEYS_PACKED4)
             return np.ascontiguousarray(k[:, 0::2] | (k[:, 1::2] << 4))
-        hp4 = [torch.from_numpy(pack4(hk[t][0])).pin_memory().numpy() for t in range(R)]
+        hp4 = [pinned(pack4(keys_r[t % R].cpu().numpy())) for t in range(R)]
 
         def host_step(t, mode, want_obs=False):
             """perform_action through the C ABI with HOST buffers: b2t_step_host copies this step's inputs from pinned host memory to
@@ -530,7 +535,7 @@ def main():
         lm = hk[0][0].shape[1]
         rate = lambda j: n * world * e2e_steps / float(e2e[j])
         out["e2e"] = {"value": rate(0), "unit": "env-steps/s", "h2d_bytes_per_step": n * (lm + 1), "d2h_bytes_per_step": n * 4, "steps": e2e_steps,
-                      "api": "b2t_step_host: pinned host keys (one code per byte, zero-terminated rows of %d) + acting player -> device, fused "
+                      "api": "b2t_step_host: pinned (b2t_host_alloc, write-combined) host keys (one code per byte, zero-terminated rows of %d) + acting player -> device, fused "
                              "step with engine-chosen seeds for the rounds that restart, reward/done/lines -> pinned host (the result "
                              "perform_action returns, tetris_environment_vector.py:79-86); observation tensors stay in HBM for the consumer. "
                              "With every buffer pinned the kernel reads the keys and writes the results through the caller's pages (zero-copy), so the "
