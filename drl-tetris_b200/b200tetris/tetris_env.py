@@ -25,7 +25,7 @@ What is reproduced (reference file:line):
   .last_winner / .recreate_state()    PythonHandle.h:315,319
   pickling                            PythonHandle.h:283-308   (unlike the reference the RNG position survives a pickle)
 Tile colours in `field` (1..7 = piece.tile, 8 = garbage) are kept after set_tile_colours(True) (B2T_FLAG_TILES); by default cells
-read 1 where the reference has 1..8 — only `field > 0` is observable through state_dict.  Not reproduced: n_players != 2.
+read 1 where the reference has 1..8 — only `field > 0` is observable through state_dict.  Not offered by this facade: n_players != 2 (the engine and the vector env take 1..4).
 """
 import gc
 import time as _time_mod
@@ -181,7 +181,8 @@ class Mask:
 
 class PythonHandle:
     def __init__(self, n_players, field_size):
-        assert int(n_players) == 2, "b200tetris builds the 2-player game (n_players=%r)" % (n_players,)
+        assert int(n_players) == 2, ("the per-env facade exchanges games as b2t_game_raw, which describes two players (n_players=%r); other "
+                                     "player counts run through b200tetris.Engine / tetris_environment_vector" % (n_players,))
         H, W = (int(v) for v in field_size)
         self._bind(_arena(H, W))
         self.masks = [Mask(), Mask()]
